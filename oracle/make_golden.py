@@ -1,0 +1,138 @@
+"""Generate tests/golden/* by running the UNMODIFIED reference (imported read-only from
+/root/reference, cv2 from the image) on deterministic synthetic frames.
+
+Run in the build container only:   python oracle/make_golden.py
+The GPU box has no /root/reference; tests there read the committed fixtures.
+
+Only two reference functions are monkey-patched, and only to serve in-memory frames with the
+reference's own sampling: ``read_frame_pairs`` and
+``extract_frame_timestamps`` (complexity_metrics.py:38-111).
+"""
+from __future__ import annotations
+
+import hashlib
+import importlib.util
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def _load_synth():
+    p = os.path.join(ROOT, "real-time-video-quality-analysis_b200", "synth.py")
+    spec = importlib.util.spec_from_file_location("vqa_synth", p)
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def _load_reference():
+    sys.path.insert(0, "/root/reference")
+    import complexity_metrics as ref  # noqa: E402  (the real thing)
+    return ref
+
+
+def patch_readers(ref, clip, fps=30.0):
+    """Serve `clip` through the reference's two VideoCapture readers, sampling as they do."""
+    n = len(clip)
+
+    def read_frame_pairs(video_path, frame_interval=10):
+        ref.validate_video_path(video_path)
+        pairs, prev = [], None
+        for count in range(1, n + 1):              # counter incremented before the test (:102-103)
+            if count % frame_interval == 0:
+                f = clip[count - 1]
+                if prev is not None:
+                    pairs.append((f, prev))
+                prev = f
+        return pairs
+
+    def extract_frame_timestamps(video_path, frame_interval=10):
+        ref.validate_video_path(video_path)
+        return [1000.0 * i / fps for i in range(n) if i % frame_interval == 0]   # test before increment (:65-69)
+
+    ref.read_frame_pairs = read_frame_pairs
+    ref.extract_frame_timestamps = extract_frame_timestamps
+
+
+def sha(a: np.ndarray) -> str:
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def per_frame(ref, clip, rw, rh):
+    import cv2
+    out = dict(
+        dct=[float(ref.process_dct_frame(f, rw, rh)) for f in clip],
+        hist=[float(ref.process_histogram_frame(f, rw, rh)) for f in clip],
+        color=[float(ref.process_color_histogram_frame(f, rw, rh)) for f in clip],
+        edge=[int(ref.process_edge_frame(f, rw, rh)) for f in clip],
+        orb=[int(ref.process_orb_frame_for_parallel(f)) for f in clip],
+        motion=[float(ref.process_frame_complexity((clip[i], clip[i - 1]))) for i in range(1, len(clip))],
+    )
+    grays = [cv2.resize(cv2.cvtColor(f, cv2.COLOR_BGR2GRAY), (rw, rh)) for f in clip]
+    out["tdct"] = [float(ref.process_temporal_dct_frame(grays[i - 1], grays[i], rw, rh)) for i in range(1, len(clip))]
+    return out
+
+
+def main():
+    import cv2
+    import pandas as pd
+    os.makedirs(GOLD, exist_ok=True)
+    S = _load_synth()
+    ref = _load_reference()
+    meta = dict(cv2=cv2.__version__, numpy=np.__version__, pandas=pd.__version__,
+                reference="/root/reference/complexity_metrics.py (unmodified, CPU branch)")
+
+    # ---- small clip, stored explicitly --------------------------------------------------
+    small = S.synth_clip(12, 96, 128, seed=7)
+    g = dict(meta=meta, small_sha=sha(small))
+    g["small_64"] = per_frame(ref, small, 64, 64)
+    g["small_native"] = per_frame(ref, small, 128, 96)
+    g["small_odd"] = per_frame(ref, small, 100, 37)
+    g["small_up"] = per_frame(ref, small, 160, 120)
+    patch_readers(ref, small)
+    for interval in (1, 3):
+        g[f"small_avg_i{interval}_64"] = [float(v) for v in ref.calculate_average_scene_complexity(
+            "synthetic.mp4", 64, 64, frame_interval=interval, num_workers=2)]
+    g["small_avg_i1_native"] = [float(v) for v in ref.calculate_average_scene_complexity(
+        "synthetic.mp4", 128, 96, frame_interval=1, num_workers=2)]
+    np.savez_compressed(os.path.join(GOLD, "small_clip.npz"), clip=small)
+
+    # ---- mid-size frames (regenerated from the seed in tests; checksum pinned) -----------
+    mid = S.synth_clip(5, 270, 480, seed=3)
+    g["mid_sha"] = sha(mid)
+    g["mid_native"] = per_frame(ref, mid, 480, 270)
+    g["mid_64"] = per_frame(ref, mid, 64, 64)
+
+    # ---- 1080p: 3 frames, full-res metrics (BASELINE.json config 2 shape) ----------------
+    hd = S.synth_clip(3, 1080, 1920, seed=0)
+    g["hd_sha"] = sha(hd)
+    g["hd_native"] = per_frame(ref, hd, 1920, 1080)
+
+    # ---- config 1 (reference CPU case): 300 x 1080p, I=10, 64x64 -------------------------
+    c1 = S.synth_clip(300, 1080, 1920, seed=0)
+    g["c1_sha_sampled"] = sha(c1[9::10])
+    patch_readers(ref, c1)
+    g["c1_avg"] = [float(v) for v in ref.calculate_average_scene_complexity(
+        "synthetic.mp4", 64, 64, frame_interval=10, num_workers=os.cpu_count())]
+
+    # ---- smoothing / framerate known answers ---------------------------------------------
+    rng = np.random.default_rng(11)
+    xs = rng.normal(size=17).tolist()
+    g["ewm_in"] = xs
+    g["ewm_out"] = [float(v) for v in ref.smooth_data(xs, 0.8)]
+    g["ewm_out_a03"] = [float(v) for v in ref.smooth_data(xs, 0.3)]
+    g["fps_pairs"] = [[0.0, 333.3333333333333], [100.0, 100.0], [50.0, 10.0], [0.0, 1000.0 / 30.0]]
+    g["fps_out"] = [float(ref.process_frame_interval_for_parallel(tuple(p))) for p in g["fps_pairs"]]
+    with open(os.path.join(GOLD, "reference_outputs.json"), "w") as f:
+        json.dump(g, f, indent=1)
+    print("wrote", GOLD)
+
+
+if __name__ == "__main__":
+    main()
