@@ -1,0 +1,152 @@
+/*
+ * vqa_b200.h -- C ABI of the B200-native per-frame scene-complexity + PSNR/SSIM path.
+ *
+ * The reference (zaki699/Real-Time-Video-Quality-Analysis) has no FFI of its own: the hot path
+ * sits behind Python module-level functions that call OpenCV / the FFmpeg CLI.  Each entry
+ * point below names the reference interface it replaces (file:line in /root/reference); the
+ * ctypes binding a maintainer would add is shown in INTEGRATION.md and shipped in
+ * real-time-video-quality-analysis_b200/_native.py.
+ *
+ * Conventions: plain pointers and sizes only; return 0 on success or a negative VQA_E_* code
+ * (never an exception); the caller owns every in/out buffer; a context owns its scratch arena
+ * and CUDA stream; one context per GPU; a context is not thread-safe.  `on_device != 0` means
+ * the input pointers are device pointers on the context's GPU, otherwise host pointers (the
+ * library stages them through its own pinned ring).  Outputs are always host memory and are
+ * valid when the call returns.
+ */
+#ifndef VQA_B200_H
+#define VQA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VQA_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define VQA_API __attribute__((visibility("default")))
+#else
+#define VQA_API
+#endif
+
+enum {
+    VQA_OK = 0,
+    VQA_E_INVALID = -1,   /* bad argument */
+    VQA_E_CUDA = -2,      /* CUDA runtime / driver error: see vqa_last_error() */
+    VQA_E_NOMEM = -3,     /* device or pinned allocation failed */
+    VQA_E_UNSUPPORTED = -4
+};
+
+/* metrics_mask bits of vqa_cfg (one per reference operator) */
+enum {
+    VQA_M_HIST = 1 << 0,      /* process_histogram_frame        complexity_metrics.py:392-416 */
+    VQA_M_COLOR = 1 << 1,     /* process_color_histogram_frame  complexity_metrics.py:418-475 */
+    VQA_M_EDGE = 1 << 2,      /* process_edge_frame             complexity_metrics.py:477-504 */
+    VQA_M_DCT = 1 << 3,       /* process_dct_frame              complexity_metrics.py:346-364 */
+    VQA_M_ORB = 1 << 4,       /* process_orb_frame_for_parallel complexity_metrics.py:367-389 */
+    VQA_M_MOTION = 1 << 5,    /* process_frame_complexity       complexity_metrics.py:313-343 */
+    VQA_M_TDCT = 1 << 6,      /* process_temporal_dct_frame     complexity_metrics.py:543-579 */
+    VQA_M_ALL = 0x7f
+};
+
+typedef struct vqa_ctx vqa_ctx;
+
+typedef struct vqa_cfg {
+    int32_t resize_width;     /* config.json resize_width  (video_processing.py:186) */
+    int32_t resize_height;    /* config.json resize_height (video_processing.py:187) */
+    uint32_t metrics_mask;    /* VQA_M_* */
+    int32_t dct_impl;         /* 0 = auto (tcgen05 tensor-core contraction), 1 = force fp32 SIMT check kernel */
+} vqa_cfg;
+
+/* One row per analysed frame.  Field <- reference return value. */
+typedef struct vqa_frame_metrics {
+    float hist_entropy;       /* process_histogram_frame        -> np.float32 */
+    float color_entropy;      /* process_color_histogram_frame  -> np.float32 (NaN on empty hist) */
+    float dct_energy;         /* process_dct_frame              -> np.float32 sum(dct^2) */
+    float motion;             /* process_frame_complexity((this, previous)); NaN if no previous */
+    float temporal_dct;       /* process_temporal_dct_frame(previous, this);  NaN if no previous */
+    int32_t orb_count;        /* process_orb_frame_for_parallel -> int */
+    int64_t edge_count;       /* process_edge_frame             -> np.int64 */
+    uint64_t gray_sq_sum;     /* exact sum of x^2 of the DCT input (Parseval cross-check of dct_energy) */
+} vqa_frame_metrics;
+
+/* One row per frame pair of the full-reference half. */
+typedef struct vqa_fr_metrics {
+    uint64_t sse[3];          /* per-plane sum of squared differences (vf_psnr.c compute_images_mse) */
+    double mse[3];            /* sse / (w_c*h_c) */
+    double mse_avg;           /* area-weighted (2/3, 1/6, 1/6 for yuv420p) */
+    double psnr[3];           /* 10 log10(255^2 / mse_c), +inf when mse == 0 */
+    double psnr_avg;          /* the `psnr_avg:` field parsed at video_processing.py:160 */
+    double ssim[3];           /* vf_ssim.c ssim_plane per plane */
+    double ssim_all;          /* the `All:` field parsed at video_processing.py:166 */
+} vqa_fr_metrics;
+
+/* ---- lifetime ------------------------------------------------------------------------- */
+VQA_API int vqa_abi_version(void);
+VQA_API int vqa_init(int device, vqa_ctx **out);
+VQA_API void vqa_destroy(vqa_ctx *ctx);
+VQA_API const char *vqa_last_error(const vqa_ctx *ctx);       /* ctx may be NULL: last init error */
+VQA_API int vqa_set_stream(vqa_ctx *ctx, void *cuda_stream);  /* borrow a cudaStream_t (e.g. torch's) */
+VQA_API int vqa_sync(vqa_ctx *ctx);
+VQA_API uint64_t vqa_kernel_launches(const vqa_ctx *ctx);     /* kernels launched by this context so far */
+/* device time (ms, CUDA events on the context's stream) of the named stage accumulated since
+ * the last vqa_reset_timers; stage in {"ingest","canny","dct","orb","motion","frscore","all"} */
+VQA_API int vqa_stage_ms(vqa_ctx *ctx, const char *stage, double *ms, uint64_t *launches);
+VQA_API int vqa_reset_timers(vqa_ctx *ctx, int enable);
+/* per-kernel profile (bench.py roofline leg): when enabled every launch is bracketed by CUDA events
+ * on the context's stream; the report has one line per kernel: "name launches total_ms
+ * algorithmic_bytes algorithmic_flops" (the byte/flop model is stated in DESIGN.md). */
+VQA_API int vqa_kernel_profile(vqa_ctx *ctx, int enable);
+VQA_API int vqa_kernel_report(vqa_ctx *ctx, char *buf, size_t cap);
+
+/* ---- a1-a8: per-frame and pair complexity metrics ----------------------------------------
+ * Replaces the bodies of process_frame_complexity / process_dct_frame /
+ * process_orb_frame_for_parallel / process_histogram_frame / process_color_histogram_frame /
+ * process_edge_frame / process_temporal_dct_frame (complexity_metrics.py:313-504,543-579) as
+ * driven by process_in_batches (:128-148) over the sampled frames of one clip.
+ *   bgr          n frames, uint8 HWC in B,G,R order, `frame_stride` bytes apart
+ *   halo         optional previous sampled frame (same h,w) or NULL: pair metrics of frame 0
+ *                are computed against it (frame-range sharding)
+ *   out          n rows, host memory
+ */
+VQA_API int vqa_complexity_frames(vqa_ctx *ctx, const uint8_t *bgr, int n, int h, int w, size_t frame_stride,
+                          const uint8_t *halo, int on_device, const vqa_cfg *cfg, vqa_frame_metrics *out);
+
+/* ---- a13: PSNR + SSIM of yuv420p (or any 3-plane 8-bit) frame pairs -------------------------
+ * Replaces the psnr= and ssim= filter graphs run_ffmpeg_metrics builds
+ * (video_processing.py:270-297); `main` is the distorted input [0:v], `ref` the reference
+ * [1:v].  Planes are dense stacks: plane c of frame i starts at plane[c] + i*plane_h[c]*stride[c].
+ */
+VQA_API int vqa_psnr_ssim_planar(vqa_ctx *ctx, const uint8_t *const main_planes[3], const uint8_t *const ref_planes[3],
+                         const int32_t plane_w[3], const int32_t plane_h[3], const int32_t stride[3],
+                         int n, int on_device, vqa_fr_metrics *out);
+
+/* ---- a9/a10: framerate variation + EWM-smoothed mean ----------------------------------------
+ * vqa_framerate_series: process_frame_interval_for_parallel over consecutive timestamps
+ * (complexity_metrics.py:150-165, driven at :296-298): fps[k] = 1000/(t[k+1]-t[k]) or 0.
+ * vqa_ewm_partial: np.mean(pd.Series(x).ewm(alpha, adjust=True).mean()) (:114-125, :301-310)
+ * written as a shard-summable weighted sum: returns sum_i c_{offset+i} x_i where c are the
+ * closed-form coefficients for a series of `total` elements.  Summing the
+ * partials of all shards gives the reference's smoothed mean.
+ */
+VQA_API int vqa_framerate_series(vqa_ctx *ctx, const double *timestamps_ms, int n, double *fps_out /* n-1 */);
+VQA_API int vqa_ewm_partial(vqa_ctx *ctx, const double *x, int n_local, int64_t offset, int64_t total,
+                    double alpha, double *partial_out);
+
+/* ---- debug / stage-level parity taps (tests only; device work, host results) ------------ */
+VQA_API int vqa_debug_gray(vqa_ctx *ctx, const uint8_t *bgr, int h, int w, uint8_t *gray_out);
+VQA_API int vqa_debug_resize(vqa_ctx *ctx, const uint8_t *src, int h, int w, int channels, int rw, int rh, uint8_t *dst);
+VQA_API int vqa_debug_hist(vqa_ctx *ctx, const uint8_t *bgr, int h, int w, int rw, int rh, uint32_t *hist_out /* 4*256: B,G,R,gray */);
+/* out117: 10x10 live window of the 64x64 gray, 4x4 FAST scores, keypoint count */
+VQA_API int vqa_debug_orb(vqa_ctx *ctx, const uint8_t *bgr, int h, int w, int32_t *out117);
+VQA_API int vqa_debug_canny(vqa_ctx *ctx, const uint8_t *gray, int h, int w, uint8_t *edges_out /* 0/255 */);
+VQA_API int vqa_debug_flow(vqa_ctx *ctx, const uint8_t *prev_gray, const uint8_t *next_gray, int h, int w, float *flow_out /* h*w*2 */);
+VQA_API int vqa_debug_dct(vqa_ctx *ctx, const uint8_t *gray, int h, int w, int impl, float *coef_out /* h*w */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VQA_B200_H */

@@ -1,0 +1,331 @@
+"""ctypes binding of libvqa_b200.so (include/vqa_b200.h).
+
+There is NO CPU fallback: if the shared object is missing or no sm_100 GPU is present the
+binding raises.  PyTorch is used only for device memory / streams (CUDA tensors are accepted
+as inputs and the context runs on torch's current stream).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libvqa_b200.so")
+
+M_HIST, M_COLOR, M_EDGE, M_DCT, M_ORB, M_MOTION, M_TDCT = (1 << i for i in range(7))
+M_ALL = 0x7F
+
+EXPORTS = [
+    "vqa_abi_version", "vqa_init", "vqa_destroy", "vqa_last_error", "vqa_set_stream", "vqa_sync",
+    "vqa_kernel_launches", "vqa_stage_ms", "vqa_reset_timers", "vqa_complexity_frames",
+    "vqa_psnr_ssim_planar", "vqa_framerate_series", "vqa_ewm_partial", "vqa_debug_gray",
+    "vqa_debug_resize", "vqa_debug_hist", "vqa_debug_orb", "vqa_kernel_profile", "vqa_kernel_report", "vqa_debug_canny", "vqa_debug_flow", "vqa_debug_dct",
+]
+
+
+class VqaError(RuntimeError):
+    pass
+
+
+class Cfg(C.Structure):
+    _fields_ = [("resize_width", C.c_int32), ("resize_height", C.c_int32),
+                ("metrics_mask", C.c_uint32), ("dct_impl", C.c_int32)]
+
+
+FRAME_DTYPE = np.dtype([("hist_entropy", "<f4"), ("color_entropy", "<f4"), ("dct_energy", "<f4"),
+                        ("motion", "<f4"), ("temporal_dct", "<f4"), ("orb_count", "<i4"),
+                        ("edge_count", "<i8"), ("gray_sq_sum", "<u8")], align=True)
+FR_DTYPE = np.dtype([("sse", "<u8", (3,)), ("mse", "<f8", (3,)), ("mse_avg", "<f8"), ("psnr", "<f8", (3,)),
+                     ("psnr_avg", "<f8"), ("ssim", "<f8", (3,)), ("ssim_all", "<f8")], align=True)
+assert FRAME_DTYPE.itemsize == 40 and FR_DTYPE.itemsize == 120
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def load_library():
+    """dlopen libvqa_b200.so and declare every prototype of include/vqa_b200.h."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(SO_PATH):
+            raise VqaError(
+                f"{SO_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). This package has no CPU fallback.")
+        L = C.CDLL(SO_PATH)
+        vp, u8p, i32p, f64p = C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_double)
+        L.vqa_abi_version.restype = C.c_int
+        L.vqa_init.argtypes = [C.c_int, C.POINTER(vp)]
+        L.vqa_destroy.argtypes = [vp]
+        L.vqa_destroy.restype = None
+        L.vqa_last_error.argtypes = [vp]
+        L.vqa_last_error.restype = C.c_char_p
+        L.vqa_set_stream.argtypes = [vp, vp]
+        L.vqa_sync.argtypes = [vp]
+        L.vqa_kernel_launches.argtypes = [vp]
+        L.vqa_kernel_launches.restype = C.c_uint64
+        L.vqa_stage_ms.argtypes = [vp, C.c_char_p, f64p, C.POINTER(C.c_uint64)]
+        L.vqa_reset_timers.argtypes = [vp, C.c_int]
+        L.vqa_complexity_frames.argtypes = [vp, u8p, C.c_int, C.c_int, C.c_int, C.c_size_t, u8p, C.c_int,
+                                            C.POINTER(Cfg), vp]
+        L.vqa_psnr_ssim_planar.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), i32p, i32p, i32p, C.c_int, C.c_int, vp]
+        L.vqa_framerate_series.argtypes = [vp, vp, C.c_int, vp]
+        L.vqa_ewm_partial.argtypes = [vp, vp, C.c_int, C.c_int64, C.c_int64, C.c_double, f64p]
+        L.vqa_debug_gray.argtypes = [vp, u8p, C.c_int, C.c_int, u8p]
+        L.vqa_debug_resize.argtypes = [vp, u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, u8p]
+        L.vqa_debug_hist.argtypes = [vp, u8p, C.c_int, C.c_int, C.c_int, C.c_int, vp]
+        L.vqa_debug_canny.argtypes = [vp, u8p, C.c_int, C.c_int, u8p]
+        L.vqa_debug_orb.argtypes = [vp, u8p, C.c_int, C.c_int, vp]
+        L.vqa_kernel_profile.argtypes = [vp, C.c_int]
+        L.vqa_kernel_report.argtypes = [vp, C.c_char_p, C.c_size_t]
+        L.vqa_debug_flow.argtypes = [vp, u8p, u8p, C.c_int, C.c_int, vp]
+        L.vqa_debug_dct.argtypes = [vp, u8p, C.c_int, C.c_int, C.c_int, vp]
+        if L.vqa_abi_version() != 1:
+            raise VqaError("libvqa_b200.so ABI version mismatch")
+        _lib = L
+        return L
+
+
+def _is_torch_tensor(x) -> bool:
+    return type(x).__module__.startswith("torch") and hasattr(x, "data_ptr")
+
+
+def _np_u8(a) -> np.ndarray:
+    a = np.asarray(a)
+    if a.dtype != np.uint8:
+        raise TypeError(f"expected uint8 frames, got {a.dtype}")
+    return np.ascontiguousarray(a)
+
+
+class Context:
+    """One per GPU (and per process).  Not thread-safe; guard with ``lock`` when shared."""
+
+    def __init__(self, device: int | None = None):
+        self.lib = load_library()
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", "0"))
+            try:
+                import torch
+                if torch.cuda.is_available():
+                    device = torch.cuda.current_device()
+            except Exception:
+                pass
+        self.device = device
+        h = C.c_void_p()
+        rc = self.lib.vqa_init(device, C.byref(h))
+        if rc != 0:
+            raise VqaError(f"vqa_init({device}) failed ({rc}): {self.lib.vqa_last_error(None).decode()} "
+                           "-- a B200 (sm_100) GPU is required; there is no CPU fallback")
+        self.h = h
+        self.lock = threading.RLock()
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.vqa_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ helpers
+    def _check(self, rc, what):
+        if rc != 0:
+            raise VqaError(f"{what} failed ({rc}): {self.lib.vqa_last_error(self.h).decode()}")
+
+    def use_torch_stream(self):
+        import torch
+        self._check(self.lib.vqa_set_stream(self.h, C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)),
+                    "vqa_set_stream")
+
+    def kernel_launches(self) -> int:
+        return int(self.lib.vqa_kernel_launches(self.h))
+
+    def reset_timers(self, enable=True):
+        self._check(self.lib.vqa_reset_timers(self.h, int(enable)), "vqa_reset_timers")
+
+    def stage_ms(self, stage: str):
+        ms, n = C.c_double(), C.c_uint64()
+        self._check(self.lib.vqa_stage_ms(self.h, stage.encode(), C.byref(ms), C.byref(n)), "vqa_stage_ms")
+        return ms.value, int(n.value)
+
+    def sync(self):
+        self._check(self.lib.vqa_sync(self.h), "vqa_sync")
+
+    # ------------------------------------------------------------------ a1-a8
+    def complexity_frames(self, frames, resize_width, resize_height, mask=M_ALL, halo=None, dct_impl=0):
+        """frames: (n,h,w,3) uint8 BGR -- numpy (host) or CUDA torch tensor.  Returns a structured
+        array (FRAME_DTYPE) with one row per frame."""
+        if _is_torch_tensor(frames):
+            if not frames.is_cuda:
+                frames = frames.numpy()
+        if _is_torch_tensor(frames):
+            import torch
+            if frames.dtype != torch.uint8 or frames.dim() != 4 or frames.shape[-1] != 3:
+                raise TypeError("expected a (n,h,w,3) uint8 CUDA tensor")
+            frames = frames.contiguous()
+            torch.cuda.current_stream(frames.device).synchronize()
+            n, h, w, _ = frames.shape
+            ptr, on_dev, stride = frames.data_ptr(), 1, h * w * 3
+            hptr = None
+            if halo is not None:
+                halo = halo.contiguous()
+                hptr = halo.data_ptr()
+            keep = (frames, halo)
+        else:
+            frames = _np_u8(frames)
+            if frames.ndim == 3:
+                frames = frames[None]
+            if frames.ndim != 4 or frames.shape[-1] != 3:
+                raise TypeError("expected (n,h,w,3) uint8 BGR frames")
+            n, h, w, _ = frames.shape
+            ptr, on_dev, stride = frames.ctypes.data, 0, h * w * 3
+            hptr = None
+            if halo is not None:
+                halo = _np_u8(halo)
+                if halo.shape != (h, w, 3):
+                    raise TypeError("halo frame must match the frame size")
+                hptr = halo.ctypes.data
+            keep = (frames, halo)
+        out = np.zeros(n, dtype=FRAME_DTYPE)
+        cfg = Cfg(int(resize_width), int(resize_height), int(mask), int(dct_impl))
+        with self.lock:
+            rc = self.lib.vqa_complexity_frames(self.h, C.c_void_p(ptr), n, h, w, stride,
+                                                C.c_void_p(hptr) if hptr else None, on_dev, C.byref(cfg),
+                                                C.c_void_p(out.ctypes.data))
+        self._check(rc, "vqa_complexity_frames")
+        del keep
+        return out
+
+    # ------------------------------------------------------------------ a13
+    def psnr_ssim(self, main_planes, ref_planes):
+        """main/ref: 3 planes each, [n,h_c,w_c] uint8 (numpy or CUDA tensors).  FR_DTYPE rows."""
+        on_dev = int(_is_torch_tensor(main_planes[0]) and main_planes[0].is_cuda)
+        keep, mp, rp, pw, ph, st = [], (C.c_void_p * 3)(), (C.c_void_p * 3)(), (C.c_int32 * 3)(), (C.c_int32 * 3)(), (C.c_int32 * 3)()
+        n = None
+        for i in range(3):
+            a, b = main_planes[i], ref_planes[i]
+            if on_dev:
+                a, b = a.contiguous(), b.contiguous()
+                shp = tuple(a.shape)
+                mp[i], rp[i] = a.data_ptr(), b.data_ptr()
+            else:
+                a, b = _np_u8(a), _np_u8(b)
+                shp = a.shape
+                mp[i], rp[i] = a.ctypes.data, b.ctypes.data
+            if len(shp) == 2:
+                shp = (1,) + shp
+            if tuple(b.shape)[-2:] != shp[-2:]:
+                raise TypeError("main/ref plane shapes differ")
+            n = shp[0] if n is None else n
+            if shp[0] != n:
+                raise TypeError("planes disagree on the frame count")
+            ph[i], pw[i], st[i] = shp[1], shp[2], shp[2]
+            keep += [a, b]
+        if on_dev:
+            import torch
+            torch.cuda.current_stream().synchronize()
+        out = np.zeros(n, dtype=FR_DTYPE)
+        with self.lock:
+            rc = self.lib.vqa_psnr_ssim_planar(self.h, mp, rp, pw, ph, st, n, on_dev, C.c_void_p(out.ctypes.data))
+        self._check(rc, "vqa_psnr_ssim_planar")
+        del keep
+        return out
+
+    # ------------------------------------------------------------------ a9 / a10
+    def framerate_series(self, timestamps_ms):
+        ts = np.ascontiguousarray(timestamps_ms, dtype=np.float64)
+        out = np.zeros(max(len(ts) - 1, 0), dtype=np.float64)
+        with self.lock:
+            rc = self.lib.vqa_framerate_series(self.h, C.c_void_p(ts.ctypes.data), len(ts), C.c_void_p(out.ctypes.data))
+        self._check(rc, "vqa_framerate_series")
+        return out
+
+    def ewm_partial(self, x, offset=0, total=None, alpha=0.8) -> float:
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        total = len(x) + offset if total is None else total
+        out = C.c_double()
+        with self.lock:
+            rc = self.lib.vqa_ewm_partial(self.h, C.c_void_p(x.ctypes.data) if len(x) else None, len(x),
+                                          int(offset), int(total), float(alpha), C.byref(out))
+        self._check(rc, "vqa_ewm_partial")
+        return out.value
+
+    # ------------------------------------------------------------------ debug taps (tests)
+    def debug_gray(self, frame):
+        f = _np_u8(frame)
+        out = np.empty(f.shape[:2], np.uint8)
+        self._check(self.lib.vqa_debug_gray(self.h, f.ctypes.data, f.shape[0], f.shape[1], out.ctypes.data), "debug_gray")
+        return out
+
+    def debug_resize(self, img, rw, rh):
+        s = _np_u8(img)
+        cn = 1 if s.ndim == 2 else s.shape[2]
+        out = np.empty((rh, rw) if s.ndim == 2 else (rh, rw, cn), np.uint8)
+        self._check(self.lib.vqa_debug_resize(self.h, s.ctypes.data, s.shape[0], s.shape[1], cn, rw, rh, out.ctypes.data), "debug_resize")
+        return out
+
+    def debug_hist(self, frame, rw, rh):
+        f = _np_u8(frame)
+        out = np.zeros((4, 256), np.uint32)
+        self._check(self.lib.vqa_debug_hist(self.h, f.ctypes.data, f.shape[0], f.shape[1], rw, rh, out.ctypes.data), "debug_hist")
+        return out
+
+    def debug_orb(self, frame):
+        f = _np_u8(frame)
+        out = np.zeros(117, np.int32)
+        self._check(self.lib.vqa_debug_orb(self.h, f.ctypes.data, f.shape[0], f.shape[1], out.ctypes.data), "debug_orb")
+        return out[:100].reshape(10, 10), out[100:116].reshape(4, 4), int(out[116])
+
+    def kernel_profile(self, enable=True):
+        self._check(self.lib.vqa_kernel_profile(self.h, int(enable)), "vqa_kernel_profile")
+
+    def kernel_report(self):
+        """{kernel: dict(launches, ms, bytes, flops)} since kernel_profile(True)."""
+        buf = C.create_string_buffer(1 << 16)
+        self._check(self.lib.vqa_kernel_report(self.h, buf, len(buf)), "vqa_kernel_report")
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, n, ms, b, fl = line.split()
+            out[name] = dict(launches=int(n), ms=float(ms), bytes=float(b), flops=float(fl))
+        return out
+
+    def debug_canny(self, gray):
+        g = _np_u8(gray)
+        out = np.empty_like(g)
+        self._check(self.lib.vqa_debug_canny(self.h, g.ctypes.data, g.shape[0], g.shape[1], out.ctypes.data), "debug_canny")
+        return out
+
+    def debug_flow(self, prev_gray, next_gray):
+        p, q = _np_u8(prev_gray), _np_u8(next_gray)
+        out = np.empty(p.shape + (2,), np.float32)
+        self._check(self.lib.vqa_debug_flow(self.h, p.ctypes.data, q.ctypes.data, p.shape[0], p.shape[1], out.ctypes.data), "debug_flow")
+        return out
+
+    def debug_dct(self, gray, impl=0):
+        g = _np_u8(gray)
+        out = np.empty(g.shape, np.float32)
+        self._check(self.lib.vqa_debug_dct(self.h, g.ctypes.data, g.shape[0], g.shape[1], impl, out.ctypes.data), "debug_dct")
+        return out
+
+
+_contexts: dict = {}
+_ctx_lock = threading.Lock()
+
+
+def get_context(device: int | None = None) -> Context:
+    """Process-wide context cache keyed by (pid, device)."""
+    key = (os.getpid(), device)
+    with _ctx_lock:
+        ctx = _contexts.get(key)
+        if ctx is None:
+            ctx = Context(device)
+            _contexts[key] = ctx
+            _contexts.setdefault((os.getpid(), ctx.device), ctx)
+        return ctx

@@ -1,0 +1,67 @@
+"""In-tree build of libvqa_b200.so (nvcc, sm_100a only).  ``python -m`` is not needed:
+``__graft_entry__.build()`` calls :func:`build_native`.  nvcc cross-compiles without a GPU."""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "build")
+SO = os.path.join(HERE, "libvqa_b200.so")
+SOURCES = ["api.cu", "ingest.cu", "canny.cu", "fast_orb.cu", "dct.cu", "dct_umma.cu", "farneback.cu",
+           "psnr_ssim.cu", "stats.cu"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr"]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found: libvqa_b200.so cannot be built (there is no CPU fallback)")
+
+
+def _deps_mtime() -> float:
+    hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    hdrs.append(os.path.join(os.path.dirname(HERE), "include", "vqa_b200.h"))
+    return max(os.path.getmtime(p) for p in hdrs)
+
+
+def build_native(force: bool = False, verbose: bool = False) -> str:
+    os.makedirs(OBJ, exist_ok=True)
+    nvcc = _nvcc()
+    hdr_m = _deps_mtime()
+    jobs = []
+    for s in SOURCES:
+        src, obj = os.path.join(CSRC, s), os.path.join(OBJ, s[:-3] + ".o")
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hdr_m):
+            cmd = [nvcc, *NVCC_FLAGS, "-c", src, "-o", obj]
+            if verbose:
+                cmd.insert(1, "-Xptxas=-v")
+            jobs.append(cmd)
+    def run(cmd):
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed: %s\n%s" % (" ".join(cmd), r.stderr))
+        return r.stderr
+    logs = []
+    if jobs:
+        with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
+            logs = list(ex.map(run, jobs))
+    objs = [os.path.join(OBJ, s[:-3] + ".o") for s in SOURCES]
+    if jobs or not os.path.exists(SO):
+        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", SO, *objs]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("link failed: %s" % r.stderr)
+    if verbose:
+        print("\n".join(logs))
+    return SO
+
+
+if __name__ == "__main__":
+    import sys
+    print(build_native(force="--force" in sys.argv, verbose="-v" in sys.argv))

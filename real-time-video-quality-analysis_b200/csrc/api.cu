@@ -1,0 +1,672 @@
+// extern "C" entry points of libvqa_b200.so (include/vqa_b200.h): context, scratch arena, the
+// chunked/double-buffered clip pipeline and the stage-level debug taps.
+#include <math.h>
+#include <stdarg.h>
+#include <stdlib.h>
+
+#include <algorithm>
+
+#include "vqa_common.cuh"
+
+static char g_init_err[512] = {0};
+
+namespace vqa {
+
+int set_err(vqa_ctx *c, int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(c ? c->err : g_init_err, 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+void *dev_buf(vqa_ctx *c, const char *name, size_t bytes)
+{
+    Buf &b = c->bufs[name];
+    if (b.cap >= bytes && b.p) return b.p;
+    if (b.p) {
+        cudaStreamSynchronize(c->stream);
+        if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+        cudaFree(b.p);
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    size_t cap = (bytes + 255) & ~(size_t)255;
+    cudaError_t e = cudaMalloc(&b.p, cap);
+    if (e != cudaSuccess) {
+        b.p = nullptr;
+        set_err(c, VQA_E_NOMEM, "cudaMalloc(%zu) for '%s' failed: %s", cap, name, cudaGetErrorString(e));
+        return nullptr;
+    }
+    b.cap = cap;
+    return b.p;
+}
+
+void *pinned_buf(vqa_ctx *c, const char *name, size_t bytes)
+{
+    Buf &b = c->pinned[name];
+    if (b.cap >= bytes && b.p) return b.p;
+    if (b.p) {
+        cudaStreamSynchronize(c->stream);
+        cudaFreeHost(b.p);
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    cudaError_t e = cudaMallocHost(&b.p, bytes);
+    if (e != cudaSuccess) {
+        b.p = nullptr;
+        set_err(c, VQA_E_NOMEM, "cudaMallocHost(%zu) for '%s' failed: %s", bytes, name, cudaGetErrorString(e));
+        return nullptr;
+    }
+    b.cap = bytes;
+    return b.p;
+}
+
+void stage_begin(vqa_ctx *c, const char *stage)
+{
+    if (!c->timing) return;
+    StageTimer &t = c->timers[stage];
+    if (t.used == t.ev.size()) {
+        cudaEvent_t a, b;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        t.ev.push_back({a, b});
+    }
+    t.launches -= c->launches;
+    cudaEventRecord(t.ev[t.used].first, c->stream);
+}
+
+void stage_end(vqa_ctx *c, const char *stage)
+{
+    if (!c->timing) return;
+    StageTimer &t = c->timers[stage];
+    cudaEventRecord(t.ev[t.used].second, c->stream);
+    t.launches += c->launches;
+    t.used++;
+}
+
+}  // namespace vqa
+
+using namespace vqa;
+
+extern "C" {
+
+int vqa_abi_version(void) { return VQA_ABI_VERSION; }
+
+int vqa_init(int device, vqa_ctx **out)
+{
+    if (!out) return VQA_E_INVALID;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return set_err(nullptr, VQA_E_CUDA, "no CUDA device: %s", cudaGetErrorString(e));
+    if (device < 0 || device >= count) return set_err(nullptr, VQA_E_INVALID, "device %d out of range", device);
+    if ((e = cudaSetDevice(device)) != cudaSuccess)
+        return set_err(nullptr, VQA_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    if (prop.major != 10)
+        return set_err(nullptr, VQA_E_UNSUPPORTED, "built for sm_100a; device is sm_%d%d", prop.major, prop.minor);
+    vqa_ctx *c = new vqa_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete c;
+        return set_err(nullptr, VQA_E_CUDA, "stream creation failed");
+    }
+    c->own_stream = true;
+    for (int i = 0; i < 2; i++) {
+        cudaEventCreateWithFlags(&c->ev_copy[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming);
+    }
+    *out = c;
+    return VQA_OK;
+}
+
+void vqa_destroy(vqa_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaStreamSynchronize(c->copy_stream);
+    dct_umma_release(c);
+    for (auto &kv : c->bufs) if (kv.second.p) cudaFree(kv.second.p);
+    for (auto &kv : c->pinned) if (kv.second.p) cudaFreeHost(kv.second.p);
+    for (auto &kv : c->timers) for (auto &p : kv.second.ev) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+    for (auto &kv : c->krec) for (auto &p : kv.second.ev) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+    for (int i = 0; i < 2; i++) { cudaEventDestroy(c->ev_copy[i]); cudaEventDestroy(c->ev_done[i]); }
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    cudaStreamDestroy(c->copy_stream);
+    delete c;
+}
+
+const char *vqa_last_error(const vqa_ctx *c) { return c ? c->err : g_init_err; }
+
+int vqa_set_stream(vqa_ctx *c, void *s)
+{
+    if (!c) return VQA_E_INVALID;
+    cudaStreamSynchronize(c->stream);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    c->stream = (cudaStream_t)s;
+    c->own_stream = false;
+    return VQA_OK;
+}
+
+int vqa_sync(vqa_ctx *c)
+{
+    if (!c) return VQA_E_INVALID;
+    VQA_CUDA(c, cudaStreamSynchronize(c->stream));
+    return VQA_OK;
+}
+
+uint64_t vqa_kernel_launches(const vqa_ctx *c) { return c ? c->launches : 0; }
+
+int vqa_reset_timers(vqa_ctx *c, int enable)
+{
+    if (!c) return VQA_E_INVALID;
+    cudaStreamSynchronize(c->stream);
+    for (auto &kv : c->timers) { kv.second.used = 0; kv.second.ms = 0; kv.second.launches = 0; }
+    c->timing = enable != 0;
+    return VQA_OK;
+}
+
+int vqa_kernel_profile(vqa_ctx *c, int enable)
+{
+    if (!c) return VQA_E_INVALID;
+    cudaStreamSynchronize(c->stream);
+    for (auto &kv : c->krec) { kv.second.used = 0; kv.second.bytes = 0; kv.second.flops = 0; }
+    c->ktiming = enable != 0;
+    return VQA_OK;
+}
+
+int vqa_kernel_report(vqa_ctx *c, char *buf, size_t cap)
+{
+    if (!c || !buf || cap == 0) return VQA_E_INVALID;
+    VQA_CUDA(c, cudaStreamSynchronize(c->stream));
+    size_t off = 0;
+    buf[0] = 0;
+    for (auto &kv : c->krec) {
+        if (!kv.second.used) continue;
+        double tot = 0;
+        for (size_t i = 0; i < kv.second.used; i++) {
+            float m = 0;
+            cudaEventElapsedTime(&m, kv.second.ev[i].first, kv.second.ev[i].second);
+            tot += m;
+        }
+        int w = snprintf(buf + off, cap - off, "%s %zu %.6f %.0f %.0f\n", kv.first.c_str(), kv.second.used, tot,
+                         kv.second.bytes, kv.second.flops);
+        if (w < 0 || (size_t)w >= cap - off) break;
+        off += (size_t)w;
+    }
+    return VQA_OK;
+}
+
+int vqa_stage_ms(vqa_ctx *c, const char *stage, double *ms, uint64_t *launches)
+{
+    if (!c || !stage) return VQA_E_INVALID;
+    VQA_CUDA(c, cudaStreamSynchronize(c->stream));
+    auto it = c->timers.find(stage);
+    double tot = 0;
+    uint64_t l = 0;
+    if (it != c->timers.end()) {
+        for (size_t i = 0; i < it->second.used; i++) {
+            float m = 0;
+            cudaEventElapsedTime(&m, it->second.ev[i].first, it->second.ev[i].second);
+            tot += m;
+        }
+        l = it->second.launches;
+    }
+    if (ms) *ms = tot;
+    if (launches) *launches = l;
+    return VQA_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+static int pick_chunk(vqa_ctx *c, int h, int w, int rw, int rh, unsigned mask)
+{
+    const char *env = getenv("VQA_CHUNK");
+    if (env && atoi(env) > 0) return atoi(env);
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    const double hw = (double)h * w, rr = (double)rw * rh;
+    double per = hw * 3 * 2 + hw * 2 + rr * 8;                         // input double buffer, gray, labels/state
+    if (mask & VQA_M_MOTION) per += hw * 66;                           // I, R, M, 2 x flow
+    if (mask & (VQA_M_DCT | VQA_M_TDCT)) per += rr * 16;               // X, T (hi/lo), C
+    // scratch already held by this context is reusable, so count it as free
+    size_t held = 0;
+    for (auto &kv : c->bufs) held += kv.second.cap;
+    double budget = 0.6 * ((double)free_b + (double)held);
+    int ch = (int)(budget / per);
+    return std::max(1, std::min(ch, 48));
+}
+
+int vqa_complexity_frames(vqa_ctx *c, const uint8_t *bgr, int n, int h, int w, size_t frame_stride,
+                          const uint8_t *halo, int on_device, const vqa_cfg *cfg, vqa_frame_metrics *out)
+{
+    if (!c) return VQA_E_INVALID;
+    if (!bgr || !cfg || !out || n < 0 || h <= 0 || w <= 0)
+        return set_err(c, VQA_E_INVALID, "vqa_complexity_frames: bad argument");
+    if (n == 0) return VQA_OK;
+    const int rw = cfg->resize_width, rh = cfg->resize_height;
+    if (rw <= 0 || rh <= 0) return set_err(c, VQA_E_INVALID, "resize dimensions must be positive");
+    if (frame_stride < (size_t)h * w * 3) return set_err(c, VQA_E_INVALID, "frame_stride smaller than a frame");
+    VQA_CUDA(c, cudaSetDevice(c->device));
+    const unsigned mask = cfg->metrics_mask ? cfg->metrics_mask : VQA_M_ALL;
+    const bool identity = (rw == w && rh == h);
+    const size_t HW = (size_t)h * w, RR = (size_t)rw * rh, FB = HW * 3;
+    const bool want_hist = mask & (VQA_M_HIST | VQA_M_COLOR), want_edge = mask & VQA_M_EDGE;
+    const bool want_dct = mask & (VQA_M_DCT | VQA_M_TDCT), want_tdct = mask & VQA_M_TDCT;
+    const bool want_motion = mask & VQA_M_MOTION, want_orb = mask & VQA_M_ORB;
+    const bool need_full_gray = want_motion || want_dct || (identity && (want_hist || want_edge));
+    const int CH = std::min(n, pick_chunk(c, h, w, rw, rh, mask));
+
+    // per-clip result arrays on the device
+    VQA_BUF(c, d_hent, float, "res.hent", n);
+    VQA_BUF(c, d_cent, float, "res.cent", n);
+    VQA_BUF(c, d_edge, unsigned long long, "res.edge", n);
+    VQA_BUF(c, d_energy, double, "res.energy", n + 1);
+    VQA_BUF(c, d_sq, unsigned long long, "res.sq", n + 1);
+    VQA_BUF(c, d_tdct, double, "res.tdct", n);
+    VQA_BUF(c, d_mag, double, "res.mag", n);
+    VQA_BUF(c, d_orb, int, "res.orb", n);
+    VQA_BUF(c, d_hist, uint32_t, "ing.hist", (size_t)CH * 1024);
+    VQA_BUF(c, G, uint8_t, "ing.gray", HW * (CH + 1));
+    uint8_t *gs = nullptr, *xs = nullptr;
+    if (!identity) {
+        if (want_hist || want_edge) { VQA_BUF(c, gs_, uint8_t, "ing.gray_small", RR * CH); gs = gs_; }
+        if (want_dct) { VQA_BUF(c, xs_, uint8_t, "ing.dct_in", RR * (CH + 1)); xs = xs_; }
+    }
+    float *Cbuf = nullptr;
+    if (want_dct) { VQA_BUF(c, cb_, float, "dct.coef", RR * (CH + 1)); Cbuf = cb_; }
+    uint8_t *in[2] = {nullptr, nullptr};
+    if (!on_device) {
+        VQA_BUF(c, in0, uint8_t, "in.bgr0", FB * CH);
+        VQA_BUF(c, in1, uint8_t, "in.bgr1", FB * CH);
+        in[0] = in0; in[1] = in1;
+    }
+    const int nchunks = cdiv(n, CH);
+    auto h2d_chunk = [&](int ci) -> int {
+        const int s = ci * CH, m = std::min(CH, n - s);
+        if (frame_stride == FB) {
+            VQA_CUDA(c, cudaMemcpyAsync(in[ci & 1], bgr + (size_t)s * frame_stride, FB * m, cudaMemcpyHostToDevice, c->copy_stream));
+        } else {
+            VQA_CUDA(c, cudaMemcpy2DAsync(in[ci & 1], FB, bgr + (size_t)s * frame_stride, frame_stride, FB, m,
+                                          cudaMemcpyHostToDevice, c->copy_stream));
+        }
+        VQA_CUDA(c, cudaEventRecord(c->ev_copy[ci & 1], c->copy_stream));
+        return VQA_OK;
+    };
+    stage_begin(c, "all");
+    if (!on_device) {
+        VQA_CUDA(c, cudaEventRecord(c->ev_done[0], c->stream));     // orders the copy stream after prior work
+        VQA_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_done[0], 0));
+        int rc = h2d_chunk(0);
+        if (rc) return rc;
+    }
+    bool has_prev = false;
+    int rc;
+    // halo frame -> gray slot 0 (+ DCT coefficients slot 0)
+    if (halo && (want_motion || want_tdct)) {
+        const uint8_t *hsrc = halo;
+        if (!on_device) {
+            VQA_BUF(c, hb, uint8_t, "in.halo", FB);
+            VQA_CUDA(c, cudaMemcpyAsync(hb, halo, FB, cudaMemcpyHostToDevice, c->stream));
+            hsrc = hb;
+        }
+        if ((rc = run_gray_hist(c, hsrc, 1, h, w, FB, G, nullptr))) return rc;
+        if (want_tdct) {
+            const uint8_t *x0 = G;
+            if (!identity) {
+                if ((rc = run_resize_u8(c, G, 1, h, w, 1, HW, rw, rh, xs))) return rc;
+                x0 = xs;
+            }
+            if ((rc = run_dct(c, x0, 1, rh, rw, cfg->dct_impl, Cbuf, d_energy + n))) return rc;
+        }
+        has_prev = true;
+    }
+    for (int ci = 0; ci < nchunks; ci++) {
+        const int s = ci * CH, m = std::min(CH, n - s);
+        const uint8_t *src;
+        size_t stride;
+        if (on_device) {
+            src = bgr + (size_t)s * frame_stride;
+            stride = frame_stride;
+        } else {
+            VQA_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copy[ci & 1], 0));
+            if (ci + 1 < nchunks) {
+                if (ci >= 1) VQA_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_done[(ci + 1) & 1], 0));
+                if ((rc = h2d_chunk(ci + 1))) return rc;
+            }
+            src = in[ci & 1];
+            stride = FB;
+        }
+        uint8_t *Gc = G + HW;                       // slots 1..m
+        // ---- ingest
+        stage_begin(c, "ingest");
+        if (identity) {
+            if (need_full_gray)
+                if ((rc = run_gray_hist(c, src, m, h, w, stride, Gc, want_hist ? d_hist : nullptr))) return rc;
+        } else {
+            if (need_full_gray) if ((rc = run_gray_hist(c, src, m, h, w, stride, Gc, nullptr))) return rc;
+            if (want_hist || want_edge)
+                if ((rc = run_resize_bgr_gray_hist(c, src, m, h, w, stride, rw, rh, gs, d_hist))) return rc;
+            if (want_dct) if ((rc = run_resize_u8(c, Gc, m, h, w, 1, HW, rw, rh, xs + RR))) return rc;
+        }
+        if (want_hist) if ((rc = run_entropy(c, d_hist, m, d_hent + s, d_cent + s))) return rc;
+        stage_end(c, "ingest");
+        // ---- Canny
+        if (want_edge) {
+            stage_begin(c, "canny");
+            if ((rc = run_canny(c, identity ? Gc : gs, m, rh, rw, d_edge + s, nullptr))) return rc;
+            stage_end(c, "canny");
+        }
+        // ---- ORB (64x64)
+        if (want_orb) {
+            stage_begin(c, "orb");
+            if ((rc = run_orb64(c, src, m, h, w, stride, d_orb + s))) return rc;
+            stage_end(c, "orb");
+        }
+        // ---- DCT energy + temporal L1
+        if (want_dct) {
+            stage_begin(c, "dct");
+            const uint8_t *X = identity ? Gc : xs + RR;
+            if ((rc = run_dct(c, X, m, rh, rw, cfg->dct_impl, Cbuf + RR, d_energy + s))) return rc;
+            if ((rc = run_sq_sum(c, X, m, (long)RR, d_sq + s))) return rc;
+            if (want_tdct) {
+                const int first = has_prev ? 0 : 1;
+                if (m - first > 0)
+                    if ((rc = run_abs_diff_sum(c, Cbuf + (size_t)first * RR, Cbuf + (size_t)(first + 1) * RR, m - first,
+                                               (long)RR, RR, RR, d_tdct + s + first))) return rc;
+                VQA_CUDA(c, cudaMemcpyAsync(Cbuf, Cbuf + (size_t)m * RR, sizeof(float) * RR, cudaMemcpyDeviceToDevice, c->stream));
+            }
+            stage_end(c, "dct");
+        }
+        // ---- Farneback motion
+        if (want_motion) {
+            stage_begin(c, "motion");
+            const int first = has_prev ? 0 : 1;
+            if (m - first > 0)
+                if ((rc = run_farneback(c, G + (size_t)first * HW, m - first, h, w, d_mag + s + first, nullptr))) return rc;
+            stage_end(c, "motion");
+        }
+        if (want_motion || want_tdct)
+            VQA_CUDA(c, cudaMemcpyAsync(G, G + (size_t)m * HW, HW, cudaMemcpyDeviceToDevice, c->stream));
+        if (!on_device) VQA_CUDA(c, cudaEventRecord(c->ev_done[ci & 1], c->stream));
+        has_prev = true;
+    }
+    stage_end(c, "all");
+    // ---- results -> host
+    struct Host {
+        float *hent, *cent;
+        unsigned long long *edge, *sq;
+        double *energy, *tdct, *mag;
+        int *orb;
+    } hr;
+    const size_t bytes = (size_t)n * (4 + 4 + 8 + 8 + 8 + 8 + 8 + 4) + 64;
+    uint8_t *hb = (uint8_t *)pinned_buf(c, "res.host", bytes);
+    if (!hb) return VQA_E_NOMEM;
+    hr.edge = (unsigned long long *)hb;
+    hr.sq = hr.edge + n;
+    hr.energy = (double *)(hr.sq + n);
+    hr.tdct = hr.energy + n;
+    hr.mag = hr.tdct + n;
+    hr.hent = (float *)(hr.mag + n);
+    hr.cent = hr.hent + n;
+    hr.orb = (int *)(hr.cent + n);
+    memset(hb, 0, bytes);
+#define D2H(dst, srcp, type) VQA_CUDA(c, cudaMemcpyAsync(dst, srcp, sizeof(type) * (size_t)n, cudaMemcpyDeviceToHost, c->stream))
+    if (want_hist) { D2H(hr.hent, d_hent, float); D2H(hr.cent, d_cent, float); }
+    if (want_edge) D2H(hr.edge, d_edge, unsigned long long);
+    if (want_dct) { D2H(hr.energy, d_energy, double); D2H(hr.sq, d_sq, unsigned long long); }
+    if (want_tdct) D2H(hr.tdct, d_tdct, double);
+    if (want_motion) D2H(hr.mag, d_mag, double);
+    if (want_orb) D2H(hr.orb, d_orb, int);
+#undef D2H
+    VQA_CUDA(c, cudaStreamSynchronize(c->stream));
+    const float nanf_ = nanf("");
+    for (int i = 0; i < n; i++) {
+        vqa_frame_metrics &o = out[i];
+        const bool prev_ok = (i > 0) || (halo != nullptr);
+        o.hist_entropy = (mask & VQA_M_HIST) ? hr.hent[i] : nanf_;
+        o.color_entropy = (mask & VQA_M_COLOR) ? hr.cent[i] : nanf_;
+        o.dct_energy = (mask & VQA_M_DCT) ? (float)hr.energy[i] : nanf_;
+        o.motion = (want_motion && prev_ok) ? (float)(hr.mag[i] / (double)HW) : nanf_;
+        o.temporal_dct = (want_tdct && prev_ok) ? (float)hr.tdct[i] : nanf_;
+        o.orb_count = want_orb ? hr.orb[i] : -1;
+        o.edge_count = want_edge ? (int64_t)hr.edge[i] : -1;
+        o.gray_sq_sum = want_dct ? hr.sq[i] : 0;
+    }
+    return VQA_OK;
+}
+
+int vqa_psnr_ssim_planar(vqa_ctx *c, const uint8_t *const main_planes[3], const uint8_t *const ref_planes[3],
+                         const int32_t plane_w[3], const int32_t plane_h[3], const int32_t stride[3], int n,
+                         int on_device, vqa_fr_metrics *out)
+{
+    if (!c) return VQA_E_INVALID;
+    if (!main_planes || !ref_planes || !plane_w || !plane_h || !stride || !out || n < 0)
+        return set_err(c, VQA_E_INVALID, "vqa_psnr_ssim_planar: bad argument");
+    if (n == 0) return VQA_OK;
+    VQA_CUDA(c, cudaSetDevice(c->device));
+    for (int p = 0; p < 3; p++)
+        if (!main_planes[p] || !ref_planes[p] || plane_w[p] <= 0 || plane_h[p] <= 0 || stride[p] < plane_w[p])
+            return set_err(c, VQA_E_INVALID, "vqa_psnr_ssim_planar: bad plane %d", p);
+    VQA_BUF(c, d_sse, unsigned long long, "fr.sse", (size_t)3 * n);
+    VQA_BUF(c, d_ssim, double, "fr.ssim", (size_t)3 * n);
+    stage_begin(c, "frscore");
+    size_t up_bytes = 0;
+    for (int p = 0; p < 3; p++) up_bytes = std::max(up_bytes, (size_t)plane_h[p] * stride[p]);
+    const int CH = std::min(n, 64);
+    uint8_t *buf[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    if (!on_device) {
+        VQA_BUF(c, a0, uint8_t, "fr.a0", up_bytes * CH);
+        VQA_BUF(c, b0, uint8_t, "fr.b0", up_bytes * CH);
+        VQA_BUF(c, a1, uint8_t, "fr.a1", up_bytes * CH);
+        VQA_BUF(c, b1, uint8_t, "fr.b1", up_bytes * CH);
+        buf[0][0] = a0; buf[0][1] = b0; buf[1][0] = a1; buf[1][1] = b1;
+    }
+    int rc, slot = 0;
+    if (!on_device) {
+        VQA_CUDA(c, cudaEventRecord(c->ev_done[0], c->stream));
+        VQA_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_done[0], 0));
+        VQA_CUDA(c, cudaEventRecord(c->ev_done[1], c->stream));
+    }
+    for (int p = 0; p < 3; p++) {
+        const size_t pb = (size_t)plane_h[p] * stride[p];
+        for (int s = 0; s < n; s += CH, slot ^= 1) {
+            const int m = std::min(CH, n - s);
+            const uint8_t *a = main_planes[p] + (size_t)s * pb, *b = ref_planes[p] + (size_t)s * pb;
+            if (!on_device) {
+                // copy on the copy stream once the kernel that last used this slot is done
+                VQA_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_done[slot], 0));
+                VQA_CUDA(c, cudaMemcpyAsync(buf[slot][0], a, pb * m, cudaMemcpyHostToDevice, c->copy_stream));
+                VQA_CUDA(c, cudaMemcpyAsync(buf[slot][1], b, pb * m, cudaMemcpyHostToDevice, c->copy_stream));
+                VQA_CUDA(c, cudaEventRecord(c->ev_copy[slot], c->copy_stream));
+                VQA_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copy[slot], 0));
+                a = buf[slot][0];
+                b = buf[slot][1];
+            }
+            if ((rc = run_psnr_ssim_plane(c, a, b, m, plane_h[p], plane_w[p], stride[p], d_sse + (size_t)p * n + s,
+                                          d_ssim + (size_t)p * n + s))) return rc;
+            if (!on_device) VQA_CUDA(c, cudaEventRecord(c->ev_done[slot], c->stream));
+        }
+    }
+    stage_end(c, "frscore");
+    uint8_t *hb = (uint8_t *)pinned_buf(c, "fr.host", (size_t)3 * n * 16);
+    if (!hb) return VQA_E_NOMEM;
+    unsigned long long *h_sse = (unsigned long long *)hb;
+    double *h_ssim = (double *)(h_sse + 3 * (size_t)n);
+    VQA_CUDA(c, cudaMemcpyAsync(h_sse, d_sse, sizeof(unsigned long long) * 3 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    VQA_CUDA(c, cudaMemcpyAsync(h_ssim, d_ssim, sizeof(double) * 3 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    VQA_CUDA(c, cudaStreamSynchronize(c->stream));
+    double area[3], tot = 0;
+    for (int p = 0; p < 3; p++) { area[p] = (double)plane_w[p] * plane_h[p]; tot += area[p]; }
+    for (int i = 0; i < n; i++) {
+        vqa_fr_metrics &o = out[i];
+        o.mse_avg = 0;
+        o.ssim_all = 0;
+        for (int p = 0; p < 3; p++) {
+            o.sse[p] = h_sse[(size_t)p * n + i];
+            o.mse[p] = (double)o.sse[p] / area[p];
+            o.psnr[p] = o.mse[p] == 0 ? INFINITY : 10.0 * log10(255.0 * 255.0 / o.mse[p]);
+            const int bw = plane_w[p] >> 2, bh = plane_h[p] >> 2;
+            o.ssim[p] = (bw > 1 && bh > 1) ? h_ssim[(size_t)p * n + i] / ((double)(bw - 1) * (bh - 1)) : 0.0;
+            o.mse_avg += o.mse[p] * (area[p] / tot);
+            o.ssim_all += o.ssim[p] * (area[p] / tot);
+        }
+        o.psnr_avg = o.mse_avg == 0 ? INFINITY : 10.0 * log10(255.0 * 255.0 / o.mse_avg);
+    }
+    return VQA_OK;
+}
+
+int vqa_framerate_series(vqa_ctx *c, const double *ts, int n, double *fps_out)
+{
+    if (!c) return VQA_E_INVALID;
+    if (n < 0 || (n > 0 && !ts) || (n > 1 && !fps_out)) return set_err(c, VQA_E_INVALID, "vqa_framerate_series: bad argument");
+    if (n < 2) return VQA_OK;
+    VQA_CUDA(c, cudaSetDevice(c->device));
+    VQA_BUF(c, d_ts, double, "st.ts", n);
+    VQA_BUF(c, d_fps, double, "st.fps", n);
+    VQA_CUDA(c, cudaMemcpyAsync(d_ts, ts, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    int rc = run_framerate(c, d_ts, n, d_fps);
+    if (rc) return rc;
+    VQA_CUDA(c, cudaMemcpyAsync(fps_out, d_fps, sizeof(double) * (n - 1), cudaMemcpyDeviceToHost, c->stream));
+    VQA_CUDA(c, cudaStreamSynchronize(c->stream));
+    return VQA_OK;
+}
+
+int vqa_ewm_partial(vqa_ctx *c, const double *x, int n_local, int64_t offset, int64_t total, double alpha, double *partial_out)
+{
+    if (!c) return VQA_E_INVALID;
+    if (!partial_out || n_local < 0 || offset < 0 || total < offset + n_local || !(alpha > 0 && alpha <= 1))
+        return set_err(c, VQA_E_INVALID, "vqa_ewm_partial: bad argument");
+    *partial_out = 0;
+    if (n_local == 0) return VQA_OK;
+    if (!x) return set_err(c, VQA_E_INVALID, "vqa_ewm_partial: null series");
+    VQA_CUDA(c, cudaSetDevice(c->device));
+    VQA_BUF(c, d_x, double, "st.x", n_local);
+    VQA_BUF(c, d_o, double, "st.o", 1);
+    VQA_CUDA(c, cudaMemcpyAsync(d_x, x, sizeof(double) * n_local, cudaMemcpyHostToDevice, c->stream));
+    int rc = run_ewm_partial(c, d_x, n_local, offset, total, alpha, d_o);
+    if (rc) return rc;
+    VQA_CUDA(c, cudaMemcpyAsync(partial_out, d_o, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    VQA_CUDA(c, cudaStreamSynchronize(c->stream));
+    return VQA_OK;
+}
+
+// ------------------------------------------------------------------------------ debug taps
+int vqa_debug_gray(vqa_ctx *c, const uint8_t *bgr, int h, int w, uint8_t *gray_out)
+{
+    if (!c || !bgr || !gray_out) return VQA_E_INVALID;
+    VQA_CUDA(c, cudaSetDevice(c->device));
+    const size_t HW = (size_t)h * w;
+    VQA_BUF(c, d_in, uint8_t, "dbg.in", HW * 3);
+    VQA_BUF(c, d_out, uint8_t, "dbg.out", HW * 4);
+    VQA_CUDA(c, cudaMemcpyAsync(d_in, bgr, HW * 3, cudaMemcpyHostToDevice, c->stream));
+    int rc = run_gray_hist(c, d_in, 1, h, w, HW * 3, d_out, nullptr);
+    if (rc) return rc;
+    VQA_CUDA(c, cudaMemcpyAsync(gray_out, d_out, HW, cudaMemcpyDeviceToHost, c->stream));
+    VQA_CUDA(c, cudaStreamSynchronize(c->stream));
+    return VQA_OK;
+}
+
+int vqa_debug_resize(vqa_ctx *c, const uint8_t *src, int h, int w, int cn, int rw, int rh, uint8_t *dst)
+{
+    if (!c || !src || !dst || (cn != 1 && cn != 3)) return VQA_E_INVALID;
+    VQA_CUDA(c, cudaSetDevice(c->device));
+    const size_t inb = (size_t)h * w * cn, outb = (size_t)rh * rw * cn;
+    VQA_BUF(c, d_in, uint8_t, "dbg.in", inb);
+    VQA_BUF(c, d_out, uint8_t, "dbg.out", outb);
+    VQA_CUDA(c, cudaMemcpyAsync(d_in, src, inb, cudaMemcpyHostToDevice, c->stream));
+    int rc = run_resize_u8(c, d_in, 1, h, w, cn, inb, rw, rh, d_out);
+    if (rc) return rc;
+    VQA_CUDA(c, cudaMemcpyAsync(dst, d_out, outb, cudaMemcpyDeviceToHost, c->stream));
+    VQA_CUDA(c, cudaStreamSynchronize(c->stream));
+    return VQA_OK;
+}
+
+int vqa_debug_hist(vqa_ctx *c, const uint8_t *bgr, int h, int w, int rw, int rh, uint32_t *hist_out)
+{
+    if (!c || !bgr || !hist_out) return VQA_E_INVALID;
+    VQA_CUDA(c, cudaSetDevice(c->device));
+    const size_t HW = (size_t)h * w;
+    VQA_BUF(c, d_in, uint8_t, "dbg.in", HW * 3);
+    VQA_BUF(c, d_out, uint8_t, "dbg.out", std::max(HW, (size_t)rw * rh) * 4);
+    VQA_BUF(c, d_h, uint32_t, "dbg.hist", 1024);
+    VQA_CUDA(c, cudaMemcpyAsync(d_in, bgr, HW * 3, cudaMemcpyHostToDevice, c->stream));
+    int rc = (rw == w && rh == h) ? run_gray_hist(c, d_in, 1, h, w, HW * 3, d_out, d_h)
+                                  : run_resize_bgr_gray_hist(c, d_in, 1, h, w, HW * 3, rw, rh, d_out, d_h);
+    if (rc) return rc;
+    VQA_CUDA(c, cudaMemcpyAsync(hist_out, d_h, 4096, cudaMemcpyDeviceToHost, c->stream));
+    VQA_CUDA(c, cudaStreamSynchronize(c->stream));
+    return VQA_OK;
+}
+
+int vqa_debug_orb(vqa_ctx *c, const uint8_t *bgr, int h, int w, int32_t *out117)
+{
+    if (!c || !bgr || !out117) return VQA_E_INVALID;
+    VQA_CUDA(c, cudaSetDevice(c->device));
+    const size_t HW = (size_t)h * w;
+    VQA_BUF(c, d_in, uint8_t, "dbg.in", HW * 3);
+    VQA_BUF(c, d_o, int, "dbg.orb", 117);
+    VQA_CUDA(c, cudaMemcpyAsync(d_in, bgr, HW * 3, cudaMemcpyHostToDevice, c->stream));
+    int rc = run_orb64(c, d_in, 1, h, w, HW * 3, d_o + 116, d_o);
+    if (rc) return rc;
+    VQA_CUDA(c, cudaMemcpyAsync(out117, d_o, sizeof(int) * 117, cudaMemcpyDeviceToHost, c->stream));
+    VQA_CUDA(c, cudaStreamSynchronize(c->stream));
+    return VQA_OK;
+}
+
+int vqa_debug_canny(vqa_ctx *c, const uint8_t *gray, int h, int w, uint8_t *edges_out)
+{
+    if (!c || !gray || !edges_out) return VQA_E_INVALID;
+    VQA_CUDA(c, cudaSetDevice(c->device));
+    const size_t HW = (size_t)h * w;
+    VQA_BUF(c, d_in, uint8_t, "dbg.in", HW);
+    VQA_BUF(c, d_out, uint8_t, "dbg.out", HW);
+    VQA_BUF(c, d_cnt, unsigned long long, "dbg.cnt", 1);
+    VQA_CUDA(c, cudaMemcpyAsync(d_in, gray, HW, cudaMemcpyHostToDevice, c->stream));
+    int rc = run_canny(c, d_in, 1, h, w, d_cnt, d_out);
+    if (rc) return rc;
+    VQA_CUDA(c, cudaMemcpyAsync(edges_out, d_out, HW, cudaMemcpyDeviceToHost, c->stream));
+    VQA_CUDA(c, cudaStreamSynchronize(c->stream));
+    return VQA_OK;
+}
+
+int vqa_debug_flow(vqa_ctx *c, const uint8_t *prev_gray, const uint8_t *next_gray, int h, int w, float *flow_out)
+{
+    if (!c || !prev_gray || !next_gray || !flow_out) return VQA_E_INVALID;
+    VQA_CUDA(c, cudaSetDevice(c->device));
+    const size_t HW = (size_t)h * w;
+    VQA_BUF(c, d_in, uint8_t, "dbg.in", HW * 2);
+    VQA_BUF(c, d_flow, float, "dbg.flow", HW * 2);
+    VQA_BUF(c, d_mag, double, "dbg.mag", 1);
+    VQA_CUDA(c, cudaMemcpyAsync(d_in, prev_gray, HW, cudaMemcpyHostToDevice, c->stream));
+    VQA_CUDA(c, cudaMemcpyAsync(d_in + HW, next_gray, HW, cudaMemcpyHostToDevice, c->stream));
+    int rc = run_farneback(c, d_in, 1, h, w, d_mag, d_flow);
+    if (rc) return rc;
+    VQA_CUDA(c, cudaMemcpyAsync(flow_out, d_flow, sizeof(float) * HW * 2, cudaMemcpyDeviceToHost, c->stream));
+    VQA_CUDA(c, cudaStreamSynchronize(c->stream));
+    return VQA_OK;
+}
+
+int vqa_debug_dct(vqa_ctx *c, const uint8_t *gray, int h, int w, int impl, float *coef_out)
+{
+    if (!c || !gray || !coef_out) return VQA_E_INVALID;
+    VQA_CUDA(c, cudaSetDevice(c->device));
+    const size_t HW = (size_t)h * w;
+    VQA_BUF(c, d_in, uint8_t, "dbg.in", HW);
+    VQA_BUF(c, d_c, float, "dbg.coef", HW);
+    VQA_BUF(c, d_e, double, "dbg.energy", 1);
+    VQA_CUDA(c, cudaMemcpyAsync(d_in, gray, HW, cudaMemcpyHostToDevice, c->stream));
+    int rc = run_dct(c, d_in, 1, h, w, impl, d_c, d_e);
+    if (rc) return rc;
+    VQA_CUDA(c, cudaMemcpyAsync(coef_out, d_c, sizeof(float) * HW, cudaMemcpyDeviceToHost, c->stream));
+    VQA_CUDA(c, cudaStreamSynchronize(c->stream));
+    return VQA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,198 @@
+// 2-D DCT-II (orthonormal) as the dense contraction C = D_h * X * D_w^T, the energy sum(C^2)
+// (process_dct_frame, complexity_metrics.py:346-364) and the temporal L1 sum|C_prev - C_cur|
+// (process_temporal_dct_frame, complexity_metrics.py:543-579).
+//
+// This file holds the basis generator, the fp32 SIMT contraction (the on-device check kernel,
+// `dct_impl = 1`, and the path for shapes the tensor-core kernel does not tile) and the streaming
+// |a-b| reduction.  The tcgen05/TMEM contraction lives in dct_umma.cu.
+#include "vqa_common.cuh"
+
+namespace vqa {
+
+// D[k][i] = sqrt(2/n) cos(pi (2i+1) k / 2n), row 0 = sqrt(1/n); argument reduced exactly mod 4n.
+__global__ void k_dct_basis(int n, float *__restrict__ D, int ld)
+{
+    const long total = (long)n * n;
+    for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+        const int k = (int)(e / n), i = (int)(e - (long)k * n);
+        double v;
+        if (k == 0) v = sqrt(1.0 / n);
+        else {
+            long m = ((long)(2 * i + 1) * k) % (4L * n);
+            v = sqrt(2.0 / n) * cospi((double)m / (2.0 * n));
+        }
+        D[(size_t)k * ld + i] = (float)v;
+    }
+}
+
+constexpr int GT = 64, GK = 16;
+
+// C[m][n] = sum_k A[m][k] * B[n][k]          (both operands K-contiguous)
+template <typename AT>
+__global__ void __launch_bounds__(256)
+k_gemm_nt(const AT *__restrict__ A, size_t strideA, int lda, const float *__restrict__ B, size_t strideB, int ldb,
+          float *__restrict__ C, size_t strideC, int ldc, int M, int N, int K)
+{
+    __shared__ float As[GK][GT + 4], Bs[GK][GT + 4];
+    const int z = blockIdx.z, m0 = blockIdx.y * GT, n0 = blockIdx.x * GT;
+    const AT *a = A + (size_t)z * strideA;
+    const float *b = B + (size_t)z * strideB;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    float acc[4][4] = {};
+    for (int k0 = 0; k0 < K; k0 += GK) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int e = threadIdx.x + j * 256, mm = e >> 4, kk = e & 15;
+            const int gm = m0 + mm, gn = n0 + mm, gk = k0 + kk;
+            As[kk][mm] = (gm < M && gk < K) ? (float)a[(size_t)gm * lda + gk] : 0.f;
+            Bs[kk][mm] = (gn < N && gk < K) ? b[(size_t)gn * ldb + gk] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < GK; kk++) {
+            float av[4], bv[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) { av[i] = As[kk][ty * 4 + i]; bv[i] = Bs[kk][tx * 4 + i]; }
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    float *c = C + (size_t)z * strideC;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int gm = m0 + ty * 4 + i, gn = n0 + tx * 4 + j;
+            if (gm < M && gn < N) c[(size_t)gm * ldc + gn] = acc[i][j];
+        }
+}
+
+// C[m][n] = sum_k A[m][k] * B[k][n], plus energy[z] += sum C^2
+__global__ void __launch_bounds__(256)
+k_gemm_nn_energy(const float *__restrict__ A, int lda, const float *__restrict__ B, size_t strideB, int ldb,
+                 float *__restrict__ C, size_t strideC, int ldc, int M, int N, int K, double *__restrict__ energy)
+{
+    __shared__ float As[GK][GT + 4], Bs[GK][GT + 4];
+    __shared__ double red[8];
+    const int z = blockIdx.z, m0 = blockIdx.y * GT, n0 = blockIdx.x * GT;
+    const float *b = B + (size_t)z * strideB;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    float acc[4][4] = {};
+    for (int k0 = 0; k0 < K; k0 += GK) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int e = threadIdx.x + j * 256;
+            const int mm = e >> 4, kk = e & 15, gm = m0 + mm, gk = k0 + kk;
+            As[kk][mm] = (gm < M && gk < K) ? A[(size_t)gm * lda + gk] : 0.f;
+            const int kb = e >> 6, nn = e & 63, gkb = k0 + kb, gn = n0 + nn;
+            Bs[kb][nn] = (gkb < K && gn < N) ? b[(size_t)gkb * ldb + gn] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < GK; kk++) {
+            float av[4], bv[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) { av[i] = As[kk][ty * 4 + i]; bv[i] = Bs[kk][tx * 4 + i]; }
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    float *c = C + (size_t)z * strideC;
+    double e = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int gm = m0 + ty * 4 + i, gn = n0 + tx * 4 + j;
+            if (gm < M && gn < N) {
+                c[(size_t)gm * ldc + gn] = acc[i][j];
+                e += (double)acc[i][j] * (double)acc[i][j];
+            }
+        }
+    e = warp_sum(e);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = e;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0;
+        for (int i = 0; i < 8; i++) s += red[i];
+        atomicAdd(&energy[z], s);
+    }
+}
+
+// out[z] = sum |a[z] - b[z]|   (float terms, double accumulation)
+__global__ void __launch_bounds__(256)
+k_abs_diff_sum(const float *__restrict__ a, const float *__restrict__ b, long per_frame, size_t stride_a,
+               size_t stride_b, double *__restrict__ out)
+{
+    __shared__ double red[8];
+    const int z = blockIdx.y;
+    const float *pa = a + (size_t)z * stride_a, *pb = b + (size_t)z * stride_b;
+    double acc = 0;
+    const long nvec = (((uintptr_t)pa | (uintptr_t)pb) & 15) == 0 ? per_frame / 4 : 0;
+    for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < nvec; i += (long)gridDim.x * 256) {
+        float4 x = reinterpret_cast<const float4 *>(pa)[i], y = reinterpret_cast<const float4 *>(pb)[i];
+        float s = fabsf(x.x - y.x) + fabsf(x.y - y.y) + fabsf(x.z - y.z) + fabsf(x.w - y.w);
+        acc += (double)s;
+    }
+    for (long i = nvec * 4 + (long)blockIdx.x * 256 + threadIdx.x; i < per_frame; i += (long)gridDim.x * 256)
+        acc += (double)fabsf(pa[i] - pb[i]);
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0;
+        for (int i = 0; i < 8; i++) s += red[i];
+        atomicAdd(&out[z], s);
+    }
+}
+
+static int dct_simt(vqa_ctx *c, const uint8_t *x, int n, int h, int w, float *coef, double *energy)
+{
+    VQA_BUF(c, Dw, float, "dct.Dw", (size_t)w * w);
+    VQA_BUF(c, Dh, float, "dct.Dh", (size_t)h * h);
+    VQA_BUF(c, T, float, "dct.T", (size_t)n * h * w);
+    VQA_LAUNCH(c, k_dct_basis, 296, 256, 0, w, Dw, w);
+    VQA_LAUNCH(c, k_dct_basis, 296, 256, 0, h, Dh, h);
+    // T = X * Dw^T
+    dim3 g(cdiv(w, GT), cdiv(h, GT), n);
+    VQA_BYTES(c, 5.0 * h * w * n);
+    VQA_FLOPS(c, 2.0 * h * w * w * n);
+    VQA_LAUNCH(c, k_gemm_nt<uint8_t>, g, 256, 0, x, (size_t)h * w, w, Dw, (size_t)0, w, T, (size_t)h * w, w, h, w, w);
+    // C = Dh * T
+    VQA_BYTES(c, 8.0 * h * w * n);
+    VQA_FLOPS(c, 2.0 * h * h * w * n);
+    VQA_LAUNCH(c, k_gemm_nn_energy, g, 256, 0, Dh, h, T, (size_t)h * w, w, coef, (size_t)h * w, w, h, w, h, energy);
+    return VQA_OK;
+}
+
+int run_dct(vqa_ctx *c, const uint8_t *x, int n, int h, int w, int impl, float *coef, double *energy)
+{
+    VQA_CUDA(c, cudaMemsetAsync(energy, 0, sizeof(double) * (size_t)n, c->stream));
+    if (impl == 1) return dct_simt(c, x, n, h, w, coef, energy);
+    return run_dct_umma(c, x, n, h, w, coef, energy);
+}
+
+int run_abs_diff_sum(vqa_ctx *c, const float *a, const float *b, int n, long per_frame, size_t stride_a,
+                     size_t stride_b, double *out)
+{
+    VQA_CUDA(c, cudaMemsetAsync(out, 0, sizeof(double) * (size_t)n, c->stream));
+    int bpf = cdiv(per_frame, 256 * 4 * 8);
+    if (bpf < 1) bpf = 1;
+    VQA_BYTES(c, 8.0 * per_frame * n);
+    VQA_LAUNCH(c, k_abs_diff_sum, dim3(bpf, n), 256, 0, a, b, per_frame, stride_a, stride_b, out);
+    return VQA_OK;
+}
+
+// exported for dct_umma.cu while the tensor-core kernel is being brought up
+int run_dct_simt(vqa_ctx *c, const uint8_t *x, int n, int h, int w, float *coef, double *energy)
+{
+    return dct_simt(c, x, n, h, w, coef, energy);
+}
+
+}  // namespace vqa

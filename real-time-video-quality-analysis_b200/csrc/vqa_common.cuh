@@ -1,0 +1,199 @@
+// Shared infrastructure of libvqa_b200.so: context, scratch arena, launch accounting, warp helpers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/vqa_b200.h"
+
+namespace vqa {
+
+struct Buf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct KRec {                                    // per-kernel-name profile (vqa_kernel_profile)
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
+    size_t used = 0;
+    double bytes = 0;                            // algorithmic bytes declared with VQA_BYTES
+    double flops = 0;
+};
+
+struct StageTimer {
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
+    size_t used = 0;
+    double ms = 0;
+    uint64_t launches = 0;
+};
+
+}  // namespace vqa
+
+struct vqa_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 148;
+    char err[512] = {0};
+    uint64_t launches = 0;
+    std::map<std::string, vqa::Buf> bufs;         // named grow-only device scratch
+    std::map<std::string, vqa::Buf> pinned;       // named grow-only pinned host staging
+    bool timing = false;
+    std::map<std::string, vqa::StageTimer> timers;
+    cudaEvent_t ev_copy[2] = {nullptr, nullptr};
+    cudaEvent_t ev_done[2] = {nullptr, nullptr};
+    bool ktiming = false;                         // per-kernel CUDA-event timing (bench roofline leg)
+    std::map<std::string, vqa::KRec> krec;
+    double cur_bytes = 0, cur_flops = 0;          // algorithmic traffic of the NEXT launch
+    void *umma = nullptr;                         // tensor-map cache of the tcgen05 DCT (dct_umma.cu)
+};
+
+namespace vqa {
+
+int set_err(vqa_ctx *c, int code, const char *fmt, ...);
+void *dev_buf(vqa_ctx *c, const char *name, size_t bytes);     // nullptr on failure (error set)
+void *pinned_buf(vqa_ctx *c, const char *name, size_t bytes);
+void stage_begin(vqa_ctx *c, const char *stage);
+void stage_end(vqa_ctx *c, const char *stage);
+
+#define VQA_CUDA(c, call)                                                                       \
+    do {                                                                                        \
+        cudaError_t e__ = (call);                                                               \
+        if (e__ != cudaSuccess)                                                                 \
+            return vqa::set_err((c), VQA_E_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call,  \
+                                cudaGetErrorString(e__));                                       \
+    } while (0)
+
+struct KTimer {
+    vqa_ctx *c;
+    KRec *r = nullptr;
+    KTimer(vqa_ctx *c_, const char *name) : c(c_)
+    {
+        if (!c->ktiming) { c->cur_bytes = c->cur_flops = 0; return; }
+        r = &c->krec[name];
+        if (r->used == r->ev.size()) {
+            cudaEvent_t a, b;
+            cudaEventCreate(&a);
+            cudaEventCreate(&b);
+            r->ev.push_back({a, b});
+        }
+        cudaEventRecord(r->ev[r->used].first, c->stream);
+    }
+    ~KTimer()
+    {
+        if (!r) return;
+        cudaEventRecord(r->ev[r->used].second, c->stream);
+        r->used++;
+        r->bytes += c->cur_bytes;
+        r->flops += c->cur_flops;
+        c->cur_bytes = c->cur_flops = 0;
+    }
+};
+
+// Declare the ALGORITHMIC bytes / flops of the next launch (DESIGN.md gives the per-unit model).
+#define VQA_BYTES(c, b) ((c)->cur_bytes = (double)(b))
+#define VQA_FLOPS(c, f) ((c)->cur_flops = (double)(f))
+
+// Launch + account + check.  Every kernel of the library goes through this.
+#define VQA_LAUNCH(c, kern, grid, block, smem, ...)                                             \
+    do {                                                                                        \
+        vqa::KTimer kt__((c), #kern);                                                           \
+        kern<<<(grid), (block), (smem), (c)->stream>>>(__VA_ARGS__);                            \
+        (c)->launches++;                                                                        \
+        cudaError_t e__ = cudaGetLastError();                                                   \
+        if (e__ != cudaSuccess)                                                                 \
+            return vqa::set_err((c), VQA_E_CUDA, "%s:%d launch %s -> %s", __FILE__, __LINE__,   \
+                                #kern, cudaGetErrorString(e__));                                \
+    } while (0)
+
+#define VQA_BUF(c, var, type, name, count)                                                      \
+    type *var = (type *)vqa::dev_buf((c), (name), sizeof(type) * (size_t)(count));              \
+    if (!var) return VQA_E_NOMEM
+
+static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
+
+// ---------------------------------------------------------------------------- device helpers
+__device__ __forceinline__ float warp_sum(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ unsigned long long warp_sum(unsigned long long v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ int warp_sum(int v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// 128-bit streaming load (read-once data: bypass L1 allocation)
+__device__ __forceinline__ uint4 ld_stream(const uint4 *p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// OpenCV BGR->gray, 15-bit fixed point
+__device__ __forceinline__ unsigned gray_of(unsigned b, unsigned g, unsigned r)
+{
+    return (3735u * b + 19235u * g + 9798u * r + (1u << 14)) >> 15;
+}
+
+// ---------------------------------------------------------------------------- stage launchers
+// ingest.cu
+int run_gray_hist(vqa_ctx *c, const uint8_t *bgr, int n, int h, int w, size_t frame_stride, uint8_t *gray,
+                  uint32_t *hist /* [n][4][256] or nullptr */);
+int run_resize_bgr_gray_hist(vqa_ctx *c, const uint8_t *bgr, int n, int h, int w, size_t frame_stride, int rw, int rh,
+                             uint8_t *gray_small, uint32_t *hist);
+int run_resize_u8(vqa_ctx *c, const uint8_t *src, int n, int h, int w, int cn, size_t frame_stride, int rw, int rh,
+                  uint8_t *dst);
+int run_entropy(vqa_ctx *c, const uint32_t *hist, int n, float *hist_entropy, float *color_entropy);
+int run_sq_sum(vqa_ctx *c, const uint8_t *x, int n, long per_frame, unsigned long long *out);
+// canny.cu
+int run_canny(vqa_ctx *c, const uint8_t *gray, int n, int h, int w, unsigned long long *counts /* [n] dev */,
+              uint8_t *edges_out /* optional [n][h][w] 0/255 */);
+// fast_orb.cu
+int run_orb64(vqa_ctx *c, const uint8_t *bgr, int n, int h, int w, size_t frame_stride, int *counts /* [n] dev */,
+              int *dbg = nullptr /* optional [116]: 10x10 window + 4x4 scores of frame 0 */);
+// dct.cu / dct_umma.cu
+int run_dct(vqa_ctx *c, const uint8_t *x, int n, int h, int w, int impl, float *coef /* [n][h][w] dev */,
+            double *energy /* [n] dev */);
+int run_abs_diff_sum(vqa_ctx *c, const float *a, const float *b, int n, long per_frame, size_t stride_a,
+                     size_t stride_b, double *out /* [n] dev */);
+int run_dct_umma(vqa_ctx *c, const uint8_t *x, int n, int h, int w, float *coef, double *energy);
+void dct_umma_release(vqa_ctx *c);
+// farneback.cu
+int run_farneback(vqa_ctx *c, const uint8_t *gray /* [n+1][h][w] */, int npairs, int h, int w,
+                  double *mag_sum /* [npairs] dev: sum |flow| */, float *flow_out /* optional, level-0 flow of pair 0.. */);
+// psnr_ssim.cu
+int run_psnr_ssim_plane(vqa_ctx *c, const uint8_t *a, const uint8_t *b, int n, int h, int w, int stride,
+                        unsigned long long *sse /* [n] */, double *ssim_sum /* [n] */);
+// stats.cu
+int run_framerate(vqa_ctx *c, const double *ts_dev, int n, double *fps_dev);
+int run_ewm_partial(vqa_ctx *c, const double *x_dev, int n_local, long long offset, long long total, double alpha,
+                    double *out_dev);
+
+}  // namespace vqa

@@ -1,0 +1,109 @@
+"""Frame-range sharding across the GPUs of one box (one process per GPU) -- SURVEY.md 8(e).
+
+The reference's only parallelism is a per-metric ``ProcessPoolExecutor.map`` over frames
+(complexity_metrics.py:143-147).  Here each rank owns a contiguous range of *sampled* frames plus
+a one-frame halo (the previous sampled frame) for the two pair metrics, evaluates its rows on its
+own GPU with no data-path collective, and the clip-level result -- the mean of the EWM-smoothed
+series -- is obtained as a sum of per-rank weighted partial sums (``vqa_ewm_partial``) with ONE
+all-reduce of 8 doubles + 3 integers at clip end (NCCL over NVLink on GPUs; gloo in the CPU
+tests of this host logic).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+# series, in the reference's return order (complexity_metrics.py:301-310)
+SERIES = ("motion", "dct_energy", "hist_entropy", "edge_count", "orb_count", "color_entropy", "temporal_dct")
+# first sampled-frame index that contributes to each series (App. B: s_0 is never analysed,
+# the temporal DCT starts one later)
+FIRST = {"motion": 1, "dct_energy": 1, "hist_entropy": 1, "edge_count": 1, "orb_count": 1,
+         "color_entropy": 1, "temporal_dct": 2}
+
+
+def shard_range(k_frames: int, rank: int, world: int):
+    """Contiguous [a, b) of sampled-frame indices owned by ``rank`` (balanced to +-1)."""
+    base, rem = divmod(k_frames, world)
+    a = rank * base + min(rank, rem)
+    return a, a + base + (1 if rank < rem else 0)
+
+
+def ewm_coefficients(total: int, alpha: float) -> np.ndarray:
+    """c_i with mean(ewm(x)) = sum_i c_i x_i (host closed form; the device kernel evaluates the
+    same weights).  Used by the CPU tests of the sharding logic and as a cross-check."""
+    if total == 0:
+        return np.zeros(0)
+    beta = 1.0 - alpha
+    t = np.arange(total, dtype=np.float64)
+    d = (t + 1.0) if beta == 1.0 else (1.0 - beta ** (t + 1.0)) / (1.0 - beta)
+    s = np.zeros(total)
+    acc = 0.0
+    for i in range(total - 1, -1, -1):
+        acc = 1.0 / d[i] + beta * acc
+        s[i] = acc
+    return s / total
+
+
+def local_partials(rows, a: int, k_frames: int, alpha: float, partial_fn):
+    """Per-series weighted partial sums of this rank's rows.
+
+    rows        structured array for sampled frames a .. a+len(rows)-1 (pair metrics of the
+                first row computed against the halo frame when a > 0)
+    partial_fn  (x, offset, total, alpha) -> float ; the device reduction in production
+    """
+    out = np.zeros(len(SERIES), dtype=np.float64)
+    for si, name in enumerate(SERIES):
+        first = FIRST[name]
+        total = max(k_frames - first, 0)
+        lo = max(first - a, 0)                      # rows before `first` do not enter the series
+        x = np.asarray(rows[name][lo:], dtype=np.float64)
+        if total == 0 or x.size == 0:
+            continue
+        out[si] = partial_fn(x, a + lo - first, total, alpha)
+    return out
+
+
+def reduce_partials(partials: np.ndarray, int_totals: np.ndarray, group=None, device=None):
+    """Sum the per-rank partial sums (float64) and integer side totals (int64) over the process
+    group; returns numpy arrays.  One collective each, payload < 100 bytes."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return partials, int_totals
+    dev = device if device is not None else ("cuda" if dist.get_backend(group) == "nccl" else "cpu")
+    f = torch.as_tensor(partials, dtype=torch.float64, device=dev)
+    i = torch.as_tensor(int_totals, dtype=torch.int64, device=dev)
+    dist.all_reduce(f, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(i, op=dist.ReduceOp.SUM, group=group)
+    return f.cpu().numpy(), i.cpu().numpy()
+
+
+def finalize(partials: np.ndarray, k_frames: int, framerate_mean: float):
+    """8-tuple in the reference's order; empty series -> nan (temporal DCT -> 0.0)."""
+    vals = []
+    for si, name in enumerate(SERIES):
+        total = k_frames - FIRST[name]
+        if total <= 0:
+            vals.append(0.0 if name == "temporal_dct" else float("nan"))
+        else:
+            vals.append(float(partials[si]))
+    return tuple(np.float64(v) for v in vals) + (np.float64(framerate_mean),)
+
+
+def sharded_average_scene_complexity(local_frames, a: int, k_frames: int, resize_width: int, resize_height: int,
+                                     timestamps_ms, halo=None, alpha: float = 0.8, group=None, ctx=None):
+    """Multi-GPU ``calculate_average_scene_complexity`` for pre-decoded sampled frames.
+
+    local_frames  (m,h,w,3) uint8 (host or CUDA tensor): sampled frames a .. a+m-1 of the clip
+    halo          sampled frame a-1 (required when a > 0)
+    timestamps_ms the clip's sampled timestamps (every rank holds them: a few bytes per frame)
+    """
+    from . import _native as N
+    ctx = ctx or N.get_context()
+    rows = ctx.complexity_frames(local_frames, resize_width, resize_height, N.M_ALL, halo=halo if a > 0 else None)
+    partials = local_partials(rows, a, k_frames, alpha, ctx.ewm_partial)
+    ints = np.array([int(rows["edge_count"][max(1 - a, 0):].sum()), int(rows["orb_count"][max(1 - a, 0):].sum()),
+                     len(rows)], dtype=np.int64)
+    partials, ints = reduce_partials(partials, ints, group)
+    fps = ctx.framerate_series(timestamps_ms) if len(timestamps_ms) > 1 else np.zeros(0)
+    fr = ctx.ewm_partial(fps, 0, len(fps), alpha) if len(fps) else float("nan")
+    return finalize(partials, k_frames, fr), ints

@@ -1,0 +1,261 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the committed golden
+fixtures of the real reference.  Integer work is bit-exact; floating-point aggregates within the
+tolerance BASELINE.json states (<= 1e-4 relative for PSNR/SSIM/DCT/motion)."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from oracle import c_oracle as CO
+from oracle import np_oracle as NO
+from oracle import ref_port as RP
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-4           # north_star tolerance for DCT / motion / PSNR / SSIM aggregates
+
+
+@pytest.fixture(scope="module")
+def ctx(vqa):
+    from rtvqa_b200 import _native as N
+    c = N.Context(0)
+    yield c
+    c.close()
+
+
+def _frames():
+    rng = np.random.default_rng(42)
+    noise = rng.integers(0, 256, (75, 101, 3), dtype=np.uint8)
+    flat = np.full((64, 80, 3), 37, np.uint8)
+    grad = np.stack([np.tile(np.arange(200, dtype=np.uint8), (120, 1))] * 3, axis=2)
+    grad[..., 1] = grad[..., 1][::-1]
+    return dict(noise=noise, flat=flat, grad=np.ascontiguousarray(grad))
+
+
+# ------------------------------------------------------------------ a1: gray / resize (bit-exact)
+@pytest.mark.parametrize("name", ["noise", "flat", "grad"])
+def test_gray_bit_exact(ctx, name):
+    f = _frames()[name]
+    assert np.array_equal(ctx.debug_gray(f), NO.bgr2gray(f))
+
+
+def test_gray_all_sizes_and_tail(ctx, synth):
+    for h, w in [(1, 1), (3, 5), (17, 33), (64, 64), (270, 480)]:
+        f = np.random.default_rng(h * 131 + w).integers(0, 256, (h, w, 3), dtype=np.uint8)
+        assert np.array_equal(ctx.debug_gray(f), NO.bgr2gray(f)), (h, w)
+
+
+@pytest.mark.parametrize("dw,dh", [(64, 64), (100, 37), (202, 150), (333, 555), (1, 1), (101, 75)])
+def test_resize_bit_exact(ctx, dw, dh):
+    f = _frames()["noise"]
+    assert np.array_equal(ctx.debug_resize(f, dw, dh), NO.resize_linear_u8(f, dw, dh))
+    g = NO.bgr2gray(f)
+    assert np.array_equal(ctx.debug_resize(g, dw, dh), NO.resize_linear_u8(g, dw, dh))
+
+
+# ------------------------------------------------------------------ a2/a3: histograms (bit-exact)
+@pytest.mark.parametrize("name", ["noise", "flat", "grad"])
+@pytest.mark.parametrize("resize", [None, (64, 64), (50, 31)])
+def test_histograms_bit_exact(ctx, name, resize):
+    f = _frames()[name]
+    rw, rh = resize if resize else (f.shape[1], f.shape[0])
+    got = ctx.debug_hist(f, rw, rh)
+    r = NO.resize_linear_u8(f, rw, rh)
+    want = np.stack([NO.hist256(r[..., 0]), NO.hist256(r[..., 1]), NO.hist256(r[..., 2]), NO.hist256(NO.bgr2gray(r))])
+    assert np.array_equal(got.astype(np.int64), want)
+    assert got.sum() == 4 * rw * rh
+
+
+# ------------------------------------------------------------------ a4: Canny (bit-exact map + count)
+def _canny_cases(synth):
+    rng = np.random.default_rng(7)
+    yield "noise", rng.integers(0, 256, (120, 160), dtype=np.uint8)
+    yield "synthetic", NO.bgr2gray(synth.synth_clip(1, 270, 480, seed=9)[0])
+    yy, xx = np.mgrid[0:200, 0:300]
+    yield "rings", (127 + 120 * np.sin(np.hypot(xx - 150, yy - 100) / 3.0)).astype(np.uint8)
+    spiral = np.zeros((128, 128), np.uint8)          # one long snaking weak edge hooked to a strong seed
+    for k in range(0, 120, 8):
+        spiral[k:k + 4, 4:124] = 60
+    spiral[0:4, 4:40] = 255
+    yield "snake", spiral
+    yield "tiny", rng.integers(0, 256, (3, 4), dtype=np.uint8)
+    yield "zero", np.zeros((33, 65), np.uint8)
+
+
+def test_canny_bit_exact(ctx, synth):
+    for name, g in _canny_cases(synth):
+        n, m = CO.canny_count(g, want_map=True)
+        got = ctx.debug_canny(g)
+        assert np.array_equal(got, m), name
+        assert int((got > 0).sum()) == int(n), name
+
+
+# ------------------------------------------------------------------ a5/a6: DCT
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("h,w", [(64, 64), (37, 100), (128, 96), (270, 480)])
+def test_dct_coefficients(ctx, impl, h, w):
+    g = np.random.default_rng(h + w).integers(0, 256, (h, w), dtype=np.uint8)
+    c = ctx.debug_dct(g, impl)
+    want = NO.dct2(g)
+    assert np.abs(c - want).max() <= 2e-6 * np.abs(want).max() + 1e-2
+    np.testing.assert_allclose(np.sum(c.astype(np.float64) ** 2), np.sum(want ** 2), rtol=1e-5)
+    # Parseval: energy equals the exact integer sum of squares
+    np.testing.assert_allclose(np.sum(c.astype(np.float64) ** 2), float(np.sum(g.astype(np.int64) ** 2)), rtol=1e-5)
+
+
+# ------------------------------------------------------------------ a7: Farneback flow
+@pytest.mark.parametrize("h,w,seed", [(96, 128, 7), (270, 480, 3), (135, 241, 4)])
+def test_farneback_flow_and_mean(ctx, synth, h, w, seed):
+    clip = synth.synth_clip(2, h, w, seed=seed)
+    a, b = NO.bgr2gray(clip[0]), NO.bgr2gray(clip[1])
+    want_mean, want_flow = CO.farneback_mean_mag(a, b, want_flow=True)
+    flow = ctx.debug_flow(a, b)
+    mag = np.sqrt(flow[..., 0].astype(np.float64) ** 2 + flow[..., 1] ** 2).mean()
+    assert mag == pytest.approx(float(want_mean), rel=RTOL)
+    # per-pixel agreement is not gated (ill-conditioned flat pixels), but the bulk must agree
+    assert np.median(np.abs(flow - want_flow)) < 1e-3
+
+
+# ------------------------------------------------------------------ whole-row parity vs the real reference
+def _check_rows(rows, want, n):
+    assert [int(v) for v in rows["edge_count"]] == want["edge"][:n]
+    assert [int(v) for v in rows["orb_count"]] == want["orb"][:n]
+    np.testing.assert_allclose(rows["hist_entropy"], want["hist"][:n], rtol=2e-6)
+    np.testing.assert_allclose(rows["color_entropy"], want["color"][:n], rtol=2e-6)
+    np.testing.assert_allclose(rows["dct_energy"], want["dct"][:n], rtol=RTOL)
+    np.testing.assert_allclose(rows["motion"][1:], want["motion"][:n - 1], rtol=RTOL, atol=1e-6)
+    np.testing.assert_allclose(rows["temporal_dct"][1:], want["tdct"][:n - 1], rtol=RTOL)
+    assert np.isnan(rows["motion"][0]) and np.isnan(rows["temporal_dct"][0])
+
+
+@pytest.mark.parametrize("key,rw,rh", [("small_64", 64, 64), ("small_native", 128, 96),
+                                        ("small_odd", 100, 37), ("small_up", 160, 120)])
+def test_rows_vs_reference_golden_small(ctx, golden, small_clip, key, rw, rh):
+    rows = ctx.complexity_frames(small_clip, rw, rh)
+    _check_rows(rows, golden[key], len(small_clip))
+    # Parseval self-check carried in the row
+    np.testing.assert_allclose(rows["dct_energy"], rows["gray_sq_sum"].astype(np.float64), rtol=1e-5)
+
+
+def test_rows_vs_reference_golden_mid_and_hd(ctx, golden, synth):
+    mid = synth.synth_clip(5, 270, 480, seed=3)
+    assert hashlib.sha256(mid.tobytes()).hexdigest() == golden["mid_sha"]
+    _check_rows(ctx.complexity_frames(mid, 480, 270), golden["mid_native"], 5)
+    _check_rows(ctx.complexity_frames(mid, 64, 64), golden["mid_64"], 5)
+    hd = synth.synth_clip(3, 1080, 1920, seed=0)
+    assert hashlib.sha256(hd.tobytes()).hexdigest() == golden["hd_sha"]
+    _check_rows(ctx.complexity_frames(hd, 1920, 1080), golden["hd_native"], 3)
+
+
+def test_halo_and_chunking_invariance(ctx, small_clip, monkeypatch):
+    """Shard-count invariance: splitting the clip into ranges with a one-frame halo,
+    or into device chunks of any size, reproduces the single-pass rows exactly."""
+    full = ctx.complexity_frames(small_clip, 64, 64)
+    for cut in (1, 5, 11):
+        a = ctx.complexity_frames(small_clip[:cut], 64, 64)
+        b = ctx.complexity_frames(small_clip[cut:], 64, 64, halo=small_clip[cut - 1])
+        got = np.concatenate([a, b])
+        for f in full.dtype.names:
+            assert np.array_equal(got[f], full[f], equal_nan=True), (cut, f)
+    monkeypatch.setenv("VQA_CHUNK", "5")
+    chunked = ctx.complexity_frames(small_clip, 64, 64)
+    for f in full.dtype.names:
+        assert np.array_equal(chunked[f], full[f], equal_nan=True), f
+
+
+def test_device_resident_input_matches_host_input(ctx, small_clip):
+    import torch
+    t = torch.from_numpy(small_clip).cuda()
+    a = ctx.complexity_frames(t, 64, 64)
+    b = ctx.complexity_frames(small_clip, 64, 64)
+    for f in a.dtype.names:
+        assert np.array_equal(a[f], b[f], equal_nan=True), f
+
+
+def test_zero_and_constant_frames(ctx):
+    z = np.zeros((2, 48, 64, 3), np.uint8)
+    r = ctx.complexity_frames(z, 64, 64)
+    assert r["dct_energy"][0] == 0 and r["edge_count"][0] == 0 and r["orb_count"][0] == 0
+    assert r["hist_entropy"][0] == 0 and abs(r["color_entropy"][0]) < 1e-6
+    assert r["motion"][1] == 0 and r["temporal_dct"][1] == 0
+
+
+# ------------------------------------------------------------------ a13: PSNR / SSIM
+@pytest.mark.parametrize("h,w", [(72, 96), (270, 480), (1080, 1920), (70, 98)])
+def test_psnr_ssim(ctx, synth, h, w):
+    n = 2
+    (ry, ru, rv), (dy, du, dv) = synth.synth_yuv_pairs(n, h, w, seed=1)
+    got = ctx.psnr_ssim((dy, du, dv), (ry, ru, rv))
+    want = RP.psnr_ssim_frames((dy, du, dv), (ry, ru, rv))
+    mains, refs = (dy, du, dv), (ry, ru, rv)
+    for c in range(3):
+        for i in range(n):
+            assert int(got["sse"][i, c]) == CO.plane_sse(mains[c][i], refs[c][i])      # integer: exact
+    np.testing.assert_allclose(got["mse"], want["mse"], rtol=1e-12)
+    np.testing.assert_allclose(got["psnr_avg"], want["psnr_avg"], rtol=1e-9)
+    np.testing.assert_allclose(got["ssim"], want["ssim"], rtol=1e-6)
+    np.testing.assert_allclose(got["ssim_all"], want["ssim_all"], rtol=1e-6)
+    same = ctx.psnr_ssim((ry, ru, rv), (ry, ru, rv))
+    assert np.all(np.isinf(same["psnr_avg"])) and np.allclose(same["ssim_all"], 1.0)
+
+
+# ------------------------------------------------------------------ a9/a10: series
+def test_series_stats(ctx, golden):
+    x = np.array(golden["ewm_in"])
+    for alpha, key in ((0.8, "ewm_out"), (0.3, "ewm_out_a03")):
+        assert ctx.ewm_partial(x, 0, len(x), alpha) == pytest.approx(np.mean(golden[key]), rel=1e-13)
+        parts = sum(ctx.ewm_partial(x[a:b], a, len(x), alpha) for a, b in ((0, 5), (5, 6), (6, 17)))
+        assert parts == pytest.approx(np.mean(golden[key]), rel=1e-13)
+    ts = np.array([0.0, 333.3333333333333, 333.3333333333333, 300.0, 1300.0])
+    got = ctx.framerate_series(ts)
+    want = [NO.process_frame_interval_for_parallel((a, b)) for a, b in zip(ts[:-1], ts[1:])]
+    assert list(got) == want
+    assert ctx.framerate_series(1000.0 * np.arange(0, 300, 10) / 30.0)[0] == 3.0000000000000004   # README.md:72
+
+
+# ------------------------------------------------------------------ the reference-shaped API
+def test_drop_in_api_matches_reference_outputs(vqa, golden, small_clip, monkeypatch):
+    """calculate_average_scene_complexity / process_in_batches with the reference's signatures;
+    readers patched exactly as oracle/make_golden.py patches the reference's."""
+    import functools
+    from rtvqa_b200 import complexity_metrics as cm
+    n = len(small_clip)
+
+    def read_frame_pairs(video_path, frame_interval=10):
+        cm.validate_video_path(video_path)
+        idx = NO.sampled_indices(n, frame_interval)
+        return [(small_clip[idx[j]], small_clip[idx[j - 1]]) for j in range(1, len(idx))]
+
+    def extract_frame_timestamps(video_path, frame_interval=10):
+        return [1000.0 * i / 30.0 for i in range(n) if i % frame_interval == 0]
+
+    monkeypatch.setattr(cm, "read_frame_pairs", read_frame_pairs)
+    monkeypatch.setattr(cm, "extract_frame_timestamps", extract_frame_timestamps)
+    for key, rw, rh, interval in (("small_avg_i1_64", 64, 64, 1), ("small_avg_i3_64", 64, 64, 3),
+                                  ("small_avg_i1_native", 128, 96, 1)):
+        got = cm.calculate_average_scene_complexity("synthetic.mp4", rw, rh, frame_interval=interval)
+        want = golden[key]
+        assert all(isinstance(v, np.float64) for v in got)
+        np.testing.assert_allclose(got, want, rtol=RTOL)
+        assert got[3] == pytest.approx(want[3], rel=1e-12) and got[4] == pytest.approx(want[4], rel=1e-12)
+    td = cm.calculate_temporal_dct("synthetic.mp4", 64, 64, frame_interval=1)
+    assert td == pytest.approx(golden["small_avg_i1_64"][6], rel=RTOL)
+    frames = list(small_clip[:4])
+    want = golden["small_64"]
+    got = cm.process_in_batches(frames, functools.partial(cm.process_edge_frame, resize_width=64, resize_height=64), 4, 3)
+    assert got == want["edge"][:4] and all(isinstance(v, np.int64) for v in got)
+    got = cm.process_in_batches(frames, cm.process_orb_frame_for_parallel, None)
+    assert got == want["orb"][:4] and all(isinstance(v, int) for v in got)
+    got = cm.process_in_batches(frames, cm.process_dct_frame, 2, resize_width=64, resize_height=64)
+    np.testing.assert_allclose(got, want["dct"][:4], rtol=RTOL)
+    pairs = [(small_clip[i], small_clip[i - 1]) for i in range(1, 4)] + [(None, small_clip[0])]
+    got = cm.process_in_batches(pairs, cm.process_frame_complexity, 2)
+    np.testing.assert_allclose(got[:3], want["motion"][:3], rtol=RTOL)
+    assert got[3] == 0.0
+    assert cm.process_frame_complexity((small_clip[1], None)) == 0.0
+    assert float(cm.process_histogram_frame(small_clip[0], 64, 64)) == pytest.approx(want["hist"][0], rel=2e-6)
+    g0, g1 = NO.bgr2gray(small_clip[0]), NO.bgr2gray(small_clip[1])
+    assert float(cm.process_temporal_dct_frame(g0, g1, 64, 64)) == pytest.approx(
+        float(RP.o_tdct(NO.resize_linear_u8(g0, 64, 64), NO.resize_linear_u8(g1, 64, 64), 64, 64)), rel=RTOL)
+    with pytest.raises(TypeError):
+        cm.process_in_batches(frames, lambda f: 0, 2)
+    assert cm.process_frame_interval_for_parallel((0.0, 1000.0 / 30.0)) == pytest.approx(30.0)
