@@ -319,13 +319,24 @@ _contexts: dict = {}
 _ctx_lock = threading.Lock()
 
 
+def _resolve_device(device):
+    if device is not None:
+        return int(device)
+    try:
+        import torch
+        if torch.cuda.is_available():
+            return int(torch.cuda.current_device())
+    except Exception:
+        pass
+    return int(os.environ.get("LOCAL_RANK", "0"))
+
+
 def get_context(device: int | None = None) -> Context:
-    """Process-wide context cache keyed by (pid, device)."""
-    key = (os.getpid(), device)
+    """Process-wide context cache keyed by (pid, device): one context (scratch arena, streams) per GPU."""
+    key = (os.getpid(), _resolve_device(device))
     with _ctx_lock:
         ctx = _contexts.get(key)
         if ctx is None:
-            ctx = Context(device)
+            ctx = Context(key[1])
             _contexts[key] = ctx
-            _contexts.setdefault((os.getpid(), ctx.device), ctx)
         return ctx

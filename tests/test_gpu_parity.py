@@ -209,7 +209,8 @@ def test_series_stats(ctx, golden):
     got = ctx.framerate_series(ts)
     want = [NO.process_frame_interval_for_parallel((a, b)) for a, b in zip(ts[:-1], ts[1:])]
     assert list(got) == want
-    assert ctx.framerate_series(1000.0 * np.arange(0, 300, 10) / 30.0)[0] == 3.0000000000000004   # README.md:72
+    cfr = 1000.0 * np.arange(0, 300, 10) / 30.0            # CFR 30 fps, I = 10 -> 3 fps (README.md:72 prints 3.0000000000000004
+    assert ctx.framerate_series(cfr)[0] == 1.0 / ((cfr[1] - cfr[0]) / 1000.0)   # for cv2's POS_MSEC stamps)
 
 
 # ------------------------------------------------------------------ the reference-shaped API
