@@ -292,7 +292,8 @@ class Context:
         self._check(self.lib.vqa_kernel_report(self.h, buf, len(buf)), "vqa_kernel_report")
         out = {}
         for line in buf.value.decode().splitlines():
-            name, n, ms, b, fl = line.split()
+            name, n, ms, b, fl = line.rsplit(None, 4)
+            name = name.replace(' ', '').strip('()')
             out[name] = dict(launches=int(n), ms=float(ms), bytes=float(b), flops=float(fl))
         return out
 

@@ -36,13 +36,18 @@ __device__ __forceinline__ int reflect101(int p, int n)
     return p;
 }
 
-// horizontal Gaussian at (row y, column x) of the uint8 image, symmetric evaluation order
+// horizontal Gaussian at (row y, column x) of the uint8 image, symmetric evaluation order.
+// Interior pixels (the whole footprint inside the row) skip the reflect-101 index arithmetic.
 __device__ __forceinline__ float hblur_u8(const uint8_t *__restrict__ row, int x, int w, const GaussTaps &t)
 {
     const int r = t.ksz >> 1;
-    float s = t.k[r] * (float)row[x];
-    for (int i = 1; i <= r; i++)
-        s += t.k[r + i] * ((float)row[reflect101(x - i, w)] + (float)row[reflect101(x + i, w)]);
+    float s = t.k[r] * (float)__ldg(row + x);
+    if (x - r >= 0 && x + r < w) {
+        for (int i = 1; i <= r; i++) s += t.k[r + i] * ((float)__ldg(row + x - i) + (float)__ldg(row + x + i));
+    } else {
+        for (int i = 1; i <= r; i++)
+            s += t.k[r + i] * ((float)__ldg(row + reflect101(x - i, w)) + (float)__ldg(row + reflect101(x + i, w)));
+    }
     return s;
 }
 
@@ -50,9 +55,14 @@ __device__ __forceinline__ float blur_at(const uint8_t *__restrict__ img, int x,
 {
     const int r = t.ksz >> 1;
     float s = t.k[r] * hblur_u8(img + (size_t)y * w, x, w, t);
-    for (int j = 1; j <= r; j++)
-        s += t.k[r + j] * (hblur_u8(img + (size_t)reflect101(y - j, h) * w, x, w, t) +
-                           hblur_u8(img + (size_t)reflect101(y + j, h) * w, x, w, t));
+    if (y - r >= 0 && y + r < h) {
+        for (int j = 1; j <= r; j++)
+            s += t.k[r + j] * (hblur_u8(img + (size_t)(y - j) * w, x, w, t) + hblur_u8(img + (size_t)(y + j) * w, x, w, t));
+    } else {
+        for (int j = 1; j <= r; j++)
+            s += t.k[r + j] * (hblur_u8(img + (size_t)reflect101(y - j, h) * w, x, w, t) +
+                               hblur_u8(img + (size_t)reflect101(y + j, h) * w, x, w, t));
+    }
     return s;
 }
 
@@ -247,51 +257,64 @@ k_fb_matrices(const float *__restrict__ R, const float2 *__restrict__ flow, int 
 }
 
 constexpr int BS_TW = 32, BS_TH = 32, BS_R = 7;
+constexpr int BS_PW = BS_TW + 2 * BS_R;          // padded tile width (46)
 
 // FarnebackUpdateFlow_Blur: 15x15 replicate-border box mean of the 5 planes of M, then the 2x2 solve.
+// Both box passes use register sliding windows: a work item sums 15 taps once and slides (7 steps
+// vertically, 3 horizontally), ~5 shared-memory reads per output instead of 30.
 __global__ void __launch_bounds__(256)
 k_fb_blur_solve(const float *__restrict__ M, int h, int w, float2 *__restrict__ flow)
 {
-    __shared__ float tile[BS_TH + 2 * BS_R][BS_TW + 2 * BS_R + 1];
-    __shared__ float vs[BS_TH][BS_TW + 2 * BS_R + 1];
+    __shared__ float tile[BS_TH + 2 * BS_R][BS_PW + 1];
+    __shared__ float vs[BS_TH][BS_PW + 1];
     const int pair = blockIdx.z;
     const size_t plane = (size_t)h * w;
     const float *src = M + (size_t)pair * 5 * plane;
     const int tx0 = blockIdx.x * BS_TW, ty0 = blockIdx.y * BS_TH;
-    const int lx = threadIdx.x & 31, ly0 = threadIdx.x >> 5;     // each thread: column lx, rows ly0 + 8*j
+    const int oy = threadIdx.x >> 3, ox = (threadIdx.x & 7) * 4;   // each thread: row oy, 4 columns from ox
     float g[5][4];
 #pragma unroll
     for (int c = 0; c < 5; c++) {
         const float *pl = src + c * plane;
-        for (int i = threadIdx.x; i < (BS_TH + 2 * BS_R) * (BS_TW + 2 * BS_R); i += 256) {
-            const int y = i / (BS_TW + 2 * BS_R), x = i - y * (BS_TW + 2 * BS_R);
+        for (int i = threadIdx.x; i < (BS_TH + 2 * BS_R) * BS_PW; i += 256) {
+            const int y = i / BS_PW, x = i - y * BS_PW;
             const int gy = clampi(ty0 - BS_R + y, 0, h - 1), gx = clampi(tx0 - BS_R + x, 0, w - 1);
-            tile[y][x] = pl[(size_t)gy * w + gx];
+            tile[y][x] = __ldg(pl + (size_t)gy * w + gx);
         }
         __syncthreads();
-        for (int i = threadIdx.x; i < BS_TH * (BS_TW + 2 * BS_R); i += 256) {
-            const int y = i / (BS_TW + 2 * BS_R), x = i - y * (BS_TW + 2 * BS_R);
+        if (threadIdx.x < 4 * BS_PW) {                              // vertical: column x, 8 rows from y0
+            const int x = threadIdx.x % BS_PW, y0 = (threadIdx.x / BS_PW) * 8;
             float s = 0.f;
 #pragma unroll
-            for (int k = 0; k < 2 * BS_R + 1; k++) s += tile[y + k][x];
-            vs[y][x] = s;
+            for (int k = 0; k < 2 * BS_R + 1; k++) s += tile[y0 + k][x];
+            vs[y0][x] = s;
+#pragma unroll
+            for (int r = 1; r < 8; r++) {
+                s += tile[y0 + r + 2 * BS_R][x] - tile[y0 + r - 1][x];
+                vs[y0 + r][x] = s;
+            }
         }
         __syncthreads();
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int y = ly0 + 8 * j;
+        {
             float s = 0.f;
 #pragma unroll
-            for (int k = 0; k < 2 * BS_R + 1; k++) s += vs[y][lx + k];
-            g[c][j] = s;
+            for (int k = 0; k < 2 * BS_R + 1; k++) s += vs[oy][ox + k];
+            g[c][0] = s;
+#pragma unroll
+            for (int j = 1; j < 4; j++) {
+                s += vs[oy][ox + j + 2 * BS_R] - vs[oy][ox + j - 1];
+                g[c][j] = s;
+            }
         }
         __syncthreads();
     }
     const double scale = 1.0 / 225.0;
+    const int gy = ty0 + oy;
+    if (gy >= h) return;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-        const int gy = ty0 + ly0 + 8 * j, gx = tx0 + lx;
-        if (gy >= h || gx >= w) continue;
+        const int gx = tx0 + ox + j;
+        if (gx >= w) continue;
         const double g11 = g[0][j] * scale, g12 = g[1][j] * scale, g22 = g[2][j] * scale;
         const double h1 = g[3][j] * scale, h2 = g[4][j] * scale;
         const double idet = 1.0 / (g11 * g22 - g12 * g12 + 1e-3);

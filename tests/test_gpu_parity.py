@@ -96,10 +96,15 @@ def test_dct_coefficients(ctx, impl, h, w):
     g = np.random.default_rng(h + w).integers(0, 256, (h, w), dtype=np.uint8)
     c = ctx.debug_dct(g, impl)
     want = NO.dct2(g)
-    assert np.abs(c - want).max() <= 2e-6 * np.abs(want).max() + 1e-2
-    np.testing.assert_allclose(np.sum(c.astype(np.float64) ** 2), np.sum(want ** 2), rtol=1e-5)
+    # impl 1 = fp32 SIMT check kernel; impl 0 = tcgen05 contraction with bf16 hi/lo splits of D and T
+    # (16-bit effective mantissa on the DC row/column; cv2's own float32 dct is off by 4.5e-2 at 1080p)
+    abs_tol = (2e-6 if impl == 1 else 1e-5) * np.abs(want).max() + (1e-2 if impl == 1 else 5e-2)
+    assert np.abs(c - want).max() <= abs_tol
+    e_tol = 1e-5 if impl == 1 else 3e-5                       # north_star bar: 1e-4
+    np.testing.assert_allclose(np.sum(c.astype(np.float64) ** 2), np.sum(want ** 2), rtol=e_tol)
+    np.testing.assert_allclose(np.abs(c).astype(np.float64).sum(), np.abs(want).sum(), rtol=e_tol)
     # Parseval: energy equals the exact integer sum of squares
-    np.testing.assert_allclose(np.sum(c.astype(np.float64) ** 2), float(np.sum(g.astype(np.int64) ** 2)), rtol=1e-5)
+    np.testing.assert_allclose(np.sum(c.astype(np.float64) ** 2), float(np.sum(g.astype(np.int64) ** 2)), rtol=e_tol)
 
 
 # ------------------------------------------------------------------ a7: Farneback flow
@@ -133,7 +138,7 @@ def test_rows_vs_reference_golden_small(ctx, golden, small_clip, key, rw, rh):
     rows = ctx.complexity_frames(small_clip, rw, rh)
     _check_rows(rows, golden[key], len(small_clip))
     # Parseval self-check carried in the row
-    np.testing.assert_allclose(rows["dct_energy"], rows["gray_sq_sum"].astype(np.float64), rtol=1e-5)
+    np.testing.assert_allclose(rows["dct_energy"], rows["gray_sq_sum"].astype(np.float64), rtol=3e-5)
 
 
 def test_rows_vs_reference_golden_mid_and_hd(ctx, golden, synth):
