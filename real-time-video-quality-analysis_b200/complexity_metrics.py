@@ -207,6 +207,10 @@ def process_in_batches(frames, process_func, num_workers, batch_size=100, **kwar
     name = getattr(func, "__name__", repr(func))
     frames = list(frames)
     results = []
+    known = set(_FRAME_FIELDS) | {"process_frame_interval_for_parallel", "process_frame_complexity"}
+    if name not in known:
+        raise TypeError(f"process_in_batches: no device kernel is registered for {name!r}; "
+                        "this build has no CPU fallback")
     ctx = N.get_context()
     if name == "process_frame_interval_for_parallel":
         for a, b in frames:
@@ -251,8 +255,7 @@ def process_in_batches(frames, process_func, num_workers, batch_size=100, **kwar
                 for f in batch:
                     results.append(cast(ctx.complexity_frames(np.asarray(f)[None], rw, rh, mask)[field][0]))
         return results
-    raise TypeError(f"process_in_batches: no device kernel is registered for {name!r}; "
-                    "this build has no CPU fallback")
+    raise AssertionError("unreachable")
 
 
 # --------------------------------------------------------------------------- clip level

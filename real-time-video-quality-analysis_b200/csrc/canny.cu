@@ -23,6 +23,7 @@ k_canny_nms(const uint8_t *__restrict__ gray, int h, int w, int low, int high, u
 {
     __shared__ uint8_t px[CT_H + 4][CT_W + 4];
     __shared__ int mag[CT_H + 2][CT_W + 2];
+    __shared__ uint8_t st[CT_H][CT_W];
     const int frame = blockIdx.z;
     const uint8_t *g = gray + (size_t)frame * h * w;
     const int tx0 = blockIdx.x * CT_W, ty0 = blockIdx.y * CT_H;
@@ -69,9 +70,19 @@ k_canny_nms(const uint8_t *__restrict__ gray, int h, int w, int low, int high, u
             }
             if (keep) s = m > high ? 2 : 1;
         }
-        size_t o = (size_t)frame * h * w + (size_t)iy * w + ix;
-        state[o] = s;
-        if (s) label[o] = iy * w + ix;
+        st[ty][tx] = s;
+        state[(size_t)frame * h * w + (size_t)iy * w + ix] = s;
+    }
+    __syncthreads();
+    // initial label = leftmost pixel of the horizontal run inside this tile: the union-find then only
+    // has to stitch runs vertically / diagonally and across tile borders
+    for (int i = threadIdx.x; i < CT_H * CT_W; i += 256) {
+        int ty = i / CT_W, tx = i - ty * CT_W;
+        int iy = ty0 + ty, ix = tx0 + tx;
+        if (iy >= h || ix >= w || !st[ty][tx]) continue;
+        int x0 = tx;
+        while (x0 > 0 && st[ty][x0 - 1]) x0--;
+        label[(size_t)frame * h * w + (size_t)iy * w + ix] = iy * w + tx0 + x0;
     }
 }
 
@@ -105,11 +116,17 @@ k_ccl_merge(const uint8_t *__restrict__ state, int h, int w, int *__restrict__ l
     for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
         if (!s[i]) continue;
         const int y = i / w, x = i - y * w;
-        if (x > 0 && s[i - 1]) uf_union(L, i, i - 1);
+        const bool west = x > 0 && s[i - 1];
+        const bool tile_edge = (x % CT_W) == 0;
+        if (west && tile_edge) uf_union(L, i, i - 1);          // runs are pre-linked inside a tile only
         if (y > 0) {
-            if (s[i - w]) uf_union(L, i, i - w);
-            if (x > 0 && s[i - w - 1]) uf_union(L, i, i - w - 1);
-            if (x < w - 1 && s[i - w + 1]) uf_union(L, i, i - w + 1);
+            if (s[i - w]) {
+                // N(i-1) and N(i) adjacent in the same tile belong to one run, as do i-1 and i: skip the duplicate
+                if (!(west && !tile_edge && s[i - w - 1])) uf_union(L, i, i - w);
+            } else {
+                if (x > 0 && s[i - w - 1] && !(west && !tile_edge)) uf_union(L, i, i - w - 1);
+                if (x < w - 1 && s[i - w + 1]) uf_union(L, i, i - w + 1);
+            }
         }
     }
 }

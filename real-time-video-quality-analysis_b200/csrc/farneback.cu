@@ -14,6 +14,7 @@
 // of the following pair.  R, M and flow stay fp32 (reduced precision does not survive flat
 // content).  Roofline: HBM.
 #include <math.h>
+#include <stdlib.h>
 
 #include "vqa_common.cuh"
 
@@ -36,36 +37,6 @@ __device__ __forceinline__ int reflect101(int p, int n)
     return p;
 }
 
-// horizontal Gaussian at (row y, column x) of the uint8 image, symmetric evaluation order.
-// Interior pixels (the whole footprint inside the row) skip the reflect-101 index arithmetic.
-__device__ __forceinline__ float hblur_u8(const uint8_t *__restrict__ row, int x, int w, const GaussTaps &t)
-{
-    const int r = t.ksz >> 1;
-    float s = t.k[r] * (float)__ldg(row + x);
-    if (x - r >= 0 && x + r < w) {
-        for (int i = 1; i <= r; i++) s += t.k[r + i] * ((float)__ldg(row + x - i) + (float)__ldg(row + x + i));
-    } else {
-        for (int i = 1; i <= r; i++)
-            s += t.k[r + i] * ((float)__ldg(row + reflect101(x - i, w)) + (float)__ldg(row + reflect101(x + i, w)));
-    }
-    return s;
-}
-
-__device__ __forceinline__ float blur_at(const uint8_t *__restrict__ img, int x, int y, int h, int w, const GaussTaps &t)
-{
-    const int r = t.ksz >> 1;
-    float s = t.k[r] * hblur_u8(img + (size_t)y * w, x, w, t);
-    if (y - r >= 0 && y + r < h) {
-        for (int j = 1; j <= r; j++)
-            s += t.k[r + j] * (hblur_u8(img + (size_t)(y - j) * w, x, w, t) + hblur_u8(img + (size_t)(y + j) * w, x, w, t));
-    } else {
-        for (int j = 1; j <= r; j++)
-            s += t.k[r + j] * (hblur_u8(img + (size_t)reflect101(y - j, h) * w, x, w, t) +
-                               hblur_u8(img + (size_t)reflect101(y + j, h) * w, x, w, t));
-    }
-    return s;
-}
-
 __device__ __forceinline__ void lin_tap_f32(int d, int sn, int dn, bool vertical, int &i0, int &i1, float &a)
 {
     const double scale = (double)sn / (double)dn;
@@ -80,93 +51,186 @@ __device__ __forceinline__ void lin_tap_f32(int d, int sn, int dn, bool vertical
     i1 = clampi(i + 1, 0, sn - 1);
 }
 
-// mode 0: same size; 1: exact 2x decimation (INTER_AREA fast path); 2: bilinear
-__global__ void __launch_bounds__(256)
-k_fb_pyramid(const uint8_t *__restrict__ gray, int H, int W, int lh, int lw, int mode, GaussTaps taps,
-             float *__restrict__ I)
+// Source taps of one destination index.  mode 0: same size; 1: exact 2x decimation (cv2.resize
+// switches INTER_LINEAR to the INTER_AREA fast path: mean of the 2x2 block); 2: bilinear.
+__device__ __forceinline__ void py_tap(int d, int sn, int dn, int mode, bool vertical, int &p0, int &p1, float &a)
 {
-    const int frame = blockIdx.z;
+    if (mode == 0) { p0 = p1 = d; a = 0.f; }
+    else if (mode == 1) { p0 = 2 * d; p1 = 2 * d + 1; a = 0.5f; }
+    else lin_tap_f32(d, sn, dn, vertical, p0, p1, a);
+}
+
+constexpr int PY_TW = 32, PY_TH = 8;
+
+// I_k = resize_f32(GaussianBlur(float(gray), ksz, sigma, REFLECT_101), level size), one output per
+// thread, shared-memory tiled: the uint8 source region of the tile (reflect-101 applied while
+// loading) -> horizontal Gaussian at the <= 64 source columns the tile samples -> vertical Gaussian
+// at the <= 2 rows each output samples -> area / bilinear combine.  Evaluation order matches
+// OpenCV's separable float32 filter (rows then columns, centre tap + symmetric pairs).
+__global__ void __launch_bounds__(PY_TW * PY_TH)
+k_fb_pyramid(const uint8_t *__restrict__ gray, int H, int W, int lh, int lw, int mode, GaussTaps taps,
+             float *__restrict__ I, int rw_pitch)
+{
+    extern __shared__ __align__(16) uint8_t py_smem[];
+    __shared__ int xtab[2 * PY_TW];
+    const int frame = blockIdx.z, tid = threadIdx.x;
     const uint8_t *img = gray + (size_t)frame * H * W;
-    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (x >= lw || y >= lh) return;
-    float v;
-    if (mode == 0) {
-        v = blur_at(img, x, y, H, W, taps);
-    } else if (mode == 1) {
-        v = (blur_at(img, 2 * x, 2 * y, H, W, taps) + blur_at(img, 2 * x + 1, 2 * y, H, W, taps) +
-             blur_at(img, 2 * x, 2 * y + 1, H, W, taps) + blur_at(img, 2 * x + 1, 2 * y + 1, H, W, taps)) * 0.25f;
-    } else {
-        int x0, x1, y0, y1;
-        float ax, ay;
-        lin_tap_f32(x, W, lw, false, x0, x1, ax);
-        lin_tap_f32(y, H, lh, true, y0, y1, ay);
-        const float a0 = 1.f - ax, b0 = 1.f - ay;
-        float t0 = __fadd_rn(__fmul_rn(blur_at(img, x0, y0, H, W, taps), a0), __fmul_rn(blur_at(img, x1, y0, H, W, taps), ax));
-        float t1 = __fadd_rn(__fmul_rn(blur_at(img, x0, y1, H, W, taps), a0), __fmul_rn(blur_at(img, x1, y1, H, W, taps), ax));
-        v = __fadd_rn(__fmul_rn(t0, b0), __fmul_rn(t1, ay));
+    const int tx0 = blockIdx.x * PY_TW, ty0 = blockIdx.y * PY_TH;
+    const int r = taps.ksz >> 1, np = mode == 0 ? 1 : 2;
+    int p0, p1, q0, q1;
+    float fa;
+    py_tap(tx0, W, lw, mode, false, p0, q0, fa);
+    py_tap(min(tx0 + PY_TW - 1, lw - 1), W, lw, mode, false, q1, p1, fa);
+    const int x_lo = p0 - r, RW = p1 + r - x_lo + 1;
+    py_tap(ty0, H, lh, mode, true, p0, q0, fa);
+    py_tap(min(ty0 + PY_TH - 1, lh - 1), H, lh, mode, true, q1, p1, fa);
+    const int y_lo = p0 - r, RH = p1 + r - y_lo + 1;
+    uint8_t *src = py_smem;                                            // [RH][rw_pitch]
+    float *hb = reinterpret_cast<float *>(py_smem + (((size_t)RH * rw_pitch + 15) & ~(size_t)15));   // [RH][np*PY_TW]
+    if (tid < np * PY_TW) {
+        int a0, a1;
+        py_tap(min(tx0 + tid / np, lw - 1), W, lw, mode, false, a0, a1, fa);
+        xtab[tid] = ((np == 2 && (tid & 1)) ? a1 : a0) - x_lo;
     }
-    I[(size_t)frame * lh * lw + (size_t)y * lw + x] = v;
+    const int lane = tid & 31, wrp = tid >> 5;
+    for (int ry = wrp; ry < RH; ry += PY_TH) {                         // one warp per source row
+        const uint8_t *g = img + (size_t)reflect101(y_lo + ry, H) * W;
+        uint8_t *d = src + ry * rw_pitch;
+        for (int rx = lane; rx < RW; rx += 32) {
+            const int gxx = x_lo + rx;
+            d[rx] = __ldg(g + ((gxx >= 0 && gxx < W) ? gxx : reflect101(gxx, W)));
+        }
+    }
+    __syncthreads();
+    const int hbw = np * PY_TW;                                        // 32 or 64
+    {
+        const int p = tid & (hbw - 1), rstep = (PY_TW * PY_TH) / hbw;
+        const int xo = xtab[p];
+        for (int ry = tid / hbw; ry < RH; ry += rstep) {
+            const uint8_t *c = src + ry * rw_pitch + xo;
+            float s = taps.k[r] * (float)c[0];
+            for (int k = 1; k <= r; k++) s += taps.k[r + k] * ((float)c[-k] + (float)c[k]);
+            hb[ry * hbw + p] = s;
+        }
+    }
+    __syncthreads();
+    const int x = tx0 + (tid & (PY_TW - 1)), y = ty0 + tid / PY_TW;
+    if (x >= lw || y >= lh) return;
+    int ya, yb, xa, xb;
+    float ax, ay;
+    py_tap(y, H, lh, mode, true, ya, yb, ay);
+    py_tap(x, W, lw, mode, false, xa, xb, ax);
+    float v[2][2];
+    for (int wy = 0; wy < np; wy++) {
+        const int yy = (wy ? yb : ya) - y_lo;
+        for (int wx = 0; wx < np; wx++) {
+            const float *c = hb + (size_t)yy * hbw + (tid & (PY_TW - 1)) * np + wx;
+            float s = taps.k[r] * c[0];
+            for (int k = 1; k <= r; k++) s += taps.k[r + k] * (c[-k * hbw] + c[k * hbw]);
+            v[wy][wx] = s;
+        }
+    }
+    float out;
+    if (mode == 0) out = v[0][0];
+    else if (mode == 1) out = (v[0][0] + v[0][1] + v[1][0] + v[1][1]) * 0.25f;
+    else {
+        const float a0 = 1.f - ax, b0 = 1.f - ay;
+        const float t0 = __fadd_rn(__fmul_rn(v[0][0], a0), __fmul_rn(v[0][1], ax));
+        const float t1 = __fadd_rn(__fmul_rn(v[1][0], a0), __fmul_rn(v[1][1], ax));
+        out = __fadd_rn(__fmul_rn(t0, b0), __fmul_rn(t1, ay));
+    }
+    I[(size_t)frame * lh * lw + (size_t)y * lw + x] = out;
 }
 
 constexpr int PE_TW = 64, PE_TH = 16, PE_R = 5;
+constexpr int PE_P = 76;                         // tile pitch (64 + 2*5 = 74, padded so rows stay 16-byte aligned)
 
-// FarnebackPolyExp: vertical pass in float, horizontal pass with double accumulators.
+// FarnebackPolyExp.  Register-blocked: every work item produces 4 adjacent columns from 128-bit
+// shared-memory reads (vertical pass: 11 LDS.128 per 4 outputs, horizontal pass: 12 LDS.128 per 4
+// outputs).  The vertical pass is float like OpenCV's; the horizontal accumulators are double like
+// OpenCV's (ACC = double) or float (ACC = float, selectable for A/B: VQA_PE_F32=1).
+template <typename ACC>
 __global__ void __launch_bounds__(256)
 k_fb_polyexp(const float *__restrict__ I, int h, int w, PolyConst pc, float *__restrict__ R)
 {
-    __shared__ float tile[PE_TH + 2 * PE_R][PE_TW + 2 * PE_R];
-    __shared__ float v0[PE_TH][PE_TW + 2 * PE_R], v1[PE_TH][PE_TW + 2 * PE_R], v2[PE_TH][PE_TW + 2 * PE_R];
-    const int frame = blockIdx.z;
+    __shared__ __align__(16) float tile[PE_TH + 2 * PE_R][PE_P];
+    __shared__ __align__(16) float v0[PE_TH][PE_P], v1[PE_TH][PE_P], v2[PE_TH][PE_P];
+    const int frame = blockIdx.z, tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
     const float *src = I + (size_t)frame * h * w;
     const int tx0 = blockIdx.x * PE_TW, ty0 = blockIdx.y * PE_TH;
-    for (int i = threadIdx.x; i < (PE_TH + 2 * PE_R) * (PE_TW + 2 * PE_R); i += 256) {
-        const int y = i / (PE_TW + 2 * PE_R), x = i - y * (PE_TW + 2 * PE_R);
-        const int gy = clampi(ty0 - PE_R + y, 0, h - 1), gx = clampi(tx0 - PE_R + x, 0, w - 1);
-        tile[y][x] = src[(size_t)gy * w + gx];
+    for (int y = wrp; y < PE_TH + 2 * PE_R; y += 8) {
+        const float *g = src + (size_t)clampi(ty0 - PE_R + y, 0, h - 1) * w;
+        for (int x = lane; x < PE_P; x += 32) tile[y][x] = __ldg(g + clampi(tx0 - PE_R + x, 0, w - 1));
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < PE_TH * (PE_TW + 2 * PE_R); i += 256) {
-        const int y = i / (PE_TW + 2 * PE_R), x = i - y * (PE_TW + 2 * PE_R);
-        // rows are clamped to the IMAGE (replicate), which the clamped tile load reproduces only if the
-        // tile row index maps to the clamped image row: true because the load clamps gy itself.
-        float t0 = tile[y + PE_R][x] * pc.g[PE_R], t1 = 0.f, t2 = 0.f;
+    for (int i = tid; i < PE_TH * (PE_P / 4); i += 256) {
+        const int y = i / (PE_P / 4), x = (i - y * (PE_P / 4)) * 4;
+        const float4 c4 = *reinterpret_cast<const float4 *>(&tile[y + PE_R][x]);
+        float t0[4] = {c4.x * pc.g[PE_R], c4.y * pc.g[PE_R], c4.z * pc.g[PE_R], c4.w * pc.g[PE_R]};
+        float t1[4] = {0.f, 0.f, 0.f, 0.f}, t2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int k = 1; k <= PE_R; k++) {
-            const float a = tile[y + PE_R - k][x], b = tile[y + PE_R + k][x];
-            const float p = a + b;
-            t0 = t0 + pc.g[PE_R + k] * p;
-            t1 = t1 + pc.xg[PE_R + k] * (b - a);
-            t2 = t2 + pc.xxg[PE_R + k] * p;
+            const float4 a4 = *reinterpret_cast<const float4 *>(&tile[y + PE_R - k][x]);
+            const float4 b4 = *reinterpret_cast<const float4 *>(&tile[y + PE_R + k][x]);
+            const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float p = a[j] + b[j];
+                t0[j] = t0[j] + pc.g[PE_R + k] * p;
+                t1[j] = t1[j] + pc.xg[PE_R + k] * (b[j] - a[j]);
+                t2[j] = t2[j] + pc.xxg[PE_R + k] * p;
+            }
         }
-        v0[y][x] = t0; v1[y][x] = t1; v2[y][x] = t2;
+        *reinterpret_cast<float4 *>(&v0[y][x]) = make_float4(t0[0], t0[1], t0[2], t0[3]);
+        *reinterpret_cast<float4 *>(&v1[y][x]) = make_float4(t1[0], t1[1], t1[2], t1[3]);
+        *reinterpret_cast<float4 *>(&v2[y][x]) = make_float4(t2[0], t2[1], t2[2], t2[3]);
     }
     __syncthreads();
-    const size_t plane = (size_t)h * w;
-    float *dst = R + (size_t)frame * 5 * plane;
-    for (int i = threadIdx.x; i < PE_TH * PE_TW; i += 256) {
-        const int y = i / PE_TW, x = i - y * PE_TW;
-        const int gy = ty0 + y, gx = tx0 + x;
-        if (gy >= h || gx >= w) continue;
-        const int c = x + PE_R;
-        const double g0 = pc.g[PE_R];
-        double b1 = v0[y][c] * g0, b2 = 0, b3 = v1[y][c] * g0, b4 = 0, b5 = v2[y][c] * g0, b6 = 0;
+    const int y = tid >> 4, x4 = (tid & 15) * 4;
+    const int gy = ty0 + y, gx0 = tx0 + x4;
+    if (gy >= h || gx0 >= w) return;
+    float a0[16], a1[16], a2[16];                 // columns x4 .. x4+15 of the three vertical results
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const float4 p0 = *reinterpret_cast<const float4 *>(&v0[y][x4 + 4 * q]);
+        const float4 p1 = *reinterpret_cast<const float4 *>(&v1[y][x4 + 4 * q]);
+        const float4 p2 = *reinterpret_cast<const float4 *>(&v2[y][x4 + 4 * q]);
+        a0[4 * q] = p0.x; a0[4 * q + 1] = p0.y; a0[4 * q + 2] = p0.z; a0[4 * q + 3] = p0.w;
+        a1[4 * q] = p1.x; a1[4 * q + 1] = p1.y; a1[4 * q + 2] = p1.z; a1[4 * q + 3] = p1.w;
+        a2[4 * q] = p2.x; a2[4 * q + 1] = p2.y; a2[4 * q + 2] = p2.z; a2[4 * q + 3] = p2.w;
+    }
+    float o[5][4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int c = j + PE_R;
+        const ACC g0 = pc.g[PE_R];
+        ACC b1 = a0[c] * g0, b2 = 0, b3 = a1[c] * g0, b4 = 0, b5 = a2[c] * g0, b6 = 0;
 #pragma unroll
         for (int k = 1; k <= PE_R; k++) {
-            const double gk = pc.g[PE_R + k], xgk = pc.xg[PE_R + k], xxgk = pc.xxg[PE_R + k];
-            const double tg = (double)(v0[y][c + k] + v0[y][c - k]);
+            const ACC gk = pc.g[PE_R + k], xgk = pc.xg[PE_R + k], xxgk = pc.xxg[PE_R + k];
+            const ACC tg = (ACC)(a0[c + k] + a0[c - k]);
             b1 += tg * gk;
             b4 += tg * xxgk;
-            b2 += (double)(v0[y][c + k] - v0[y][c - k]) * xgk;
-            b3 += (double)(v1[y][c + k] + v1[y][c - k]) * gk;
-            b6 += (double)(v1[y][c + k] - v1[y][c - k]) * xgk;
-            b5 += (double)(v2[y][c + k] + v2[y][c - k]) * gk;
+            b2 += (ACC)(a0[c + k] - a0[c - k]) * xgk;
+            b3 += (ACC)(a1[c + k] + a1[c - k]) * gk;
+            b6 += (ACC)(a1[c + k] - a1[c - k]) * xgk;
+            b5 += (ACC)(a2[c + k] + a2[c - k]) * gk;
         }
-        const size_t o = (size_t)gy * w + gx;
-        dst[o] = (float)(b3 * pc.ig11);
-        dst[plane + o] = (float)(b2 * pc.ig11);
-        dst[2 * plane + o] = (float)(b1 * pc.ig03 + b5 * pc.ig33);
-        dst[3 * plane + o] = (float)(b1 * pc.ig03 + b4 * pc.ig33);
-        dst[4 * plane + o] = (float)(b6 * pc.ig55);
+        o[0][j] = (float)(b3 * (ACC)pc.ig11);
+        o[1][j] = (float)(b2 * (ACC)pc.ig11);
+        o[2][j] = (float)(b1 * (ACC)pc.ig03 + b5 * (ACC)pc.ig33);
+        o[3][j] = (float)(b1 * (ACC)pc.ig03 + b4 * (ACC)pc.ig33);
+        o[4][j] = (float)(b6 * (ACC)pc.ig55);
+    }
+    const size_t plane = (size_t)h * w;
+    float *dst = R + (size_t)frame * 5 * plane + (size_t)gy * w + gx0;
+    const bool vec = (w & 3) == 0 && gx0 + 4 <= w;          // planes are 256-byte aligned, w % 4 == 0 keeps rows aligned
+#pragma unroll
+    for (int ch = 0; ch < 5; ch++) {
+        if (vec) *reinterpret_cast<float4 *>(dst + ch * plane) = make_float4(o[ch][0], o[ch][1], o[ch][2], o[ch][3]);
+        else
+            for (int j = 0; j < 4; j++)
+                if (gx0 + j < w) dst[ch * plane + j] = o[ch][j];
     }
 }
 
@@ -256,72 +320,82 @@ k_fb_matrices(const float *__restrict__ R, const float2 *__restrict__ flow, int 
     for (int c = 0; c < 5; c++) dst[c * plane] = m[c];
 }
 
-constexpr int BS_TW = 32, BS_TH = 32, BS_R = 7;
-constexpr int BS_PW = BS_TW + 2 * BS_R;          // padded tile width (46)
+constexpr int MS_W = 128, MS_OUT = 112, MS_R = 7, MS_H = 96, MS_SEG = 8;
 
 // FarnebackUpdateFlow_Blur: 15x15 replicate-border box mean of the 5 planes of M, then the 2x2 solve.
-// Both box passes use register sliding windows: a work item sums 15 taps once and slides (7 steps
-// vertically, 3 horizontally), ~5 shared-memory reads per output instead of 30.
-__global__ void __launch_bounds__(256)
+// "Column marching": a block owns a strip of 112 output columns (+8 halo columns each side = 128
+// threads, one column each) and walks down 64 rows.  Every thread keeps the vertical 15-row running
+// sums of its column for the 5 planes in DOUBLE registers (OpenCV's vsum is double too: a float
+// running sum would keep eps*|edge value| of error in flat areas next to strong edges), so each row
+// costs one incoming + one outgoing load per plane.  The horizontal 15-tap sums are built from the
+// shared row of vertical sums by 70 work items (5 planes x 14 segments of 8 outputs), sliding in double.
+// shared rows are padded by one word every 8 so that the 14 segment work items of a plane (stride 8)
+// fall into distinct banks
+__device__ __forceinline__ int ms_pad(int i) { return i + (i >> 3); }
+constexpr int MS_ROWP = MS_W + MS_W / 8 + 1, MS_HSP = MS_OUT + MS_OUT / 8 + 1;
+
+__global__ void __launch_bounds__(MS_W)
 k_fb_blur_solve(const float *__restrict__ M, int h, int w, float2 *__restrict__ flow)
 {
-    __shared__ float tile[BS_TH + 2 * BS_R][BS_PW + 1];
-    __shared__ float vs[BS_TH][BS_PW + 1];
-    const int pair = blockIdx.z;
+    __shared__ float row[5][MS_ROWP];
+    __shared__ float hs[5][MS_HSP];
+    const int pair = blockIdx.z, t = threadIdx.x;
     const size_t plane = (size_t)h * w;
     const float *src = M + (size_t)pair * 5 * plane;
-    const int tx0 = blockIdx.x * BS_TW, ty0 = blockIdx.y * BS_TH;
-    const int oy = threadIdx.x >> 3, ox = (threadIdx.x & 7) * 4;   // each thread: row oy, 4 columns from ox
-    float g[5][4];
+    const int sx0 = blockIdx.x * MS_OUT, y0 = blockIdx.y * MS_H;
+    const int gx = clampi(sx0 - 8 + t, 0, w - 1);
+    const int y_end = min(y0 + MS_H, h);
+    double vs[5];
 #pragma unroll
     for (int c = 0; c < 5; c++) {
-        const float *pl = src + c * plane;
-        for (int i = threadIdx.x; i < (BS_TH + 2 * BS_R) * BS_PW; i += 256) {
-            const int y = i / BS_PW, x = i - y * BS_PW;
-            const int gy = clampi(ty0 - BS_R + y, 0, h - 1), gx = clampi(tx0 - BS_R + x, 0, w - 1);
-            tile[y][x] = __ldg(pl + (size_t)gy * w + gx);
-        }
-        __syncthreads();
-        if (threadIdx.x < 4 * BS_PW) {                              // vertical: column x, 8 rows from y0
-            const int x = threadIdx.x % BS_PW, y0 = (threadIdx.x / BS_PW) * 8;
-            float s = 0.f;
-#pragma unroll
-            for (int k = 0; k < 2 * BS_R + 1; k++) s += tile[y0 + k][x];
-            vs[y0][x] = s;
-#pragma unroll
-            for (int r = 1; r < 8; r++) {
-                s += tile[y0 + r + 2 * BS_R][x] - tile[y0 + r - 1][x];
-                vs[y0 + r][x] = s;
-            }
-        }
-        __syncthreads();
-        {
-            float s = 0.f;
-#pragma unroll
-            for (int k = 0; k < 2 * BS_R + 1; k++) s += vs[oy][ox + k];
-            g[c][0] = s;
-#pragma unroll
-            for (int j = 1; j < 4; j++) {
-                s += vs[oy][ox + j + 2 * BS_R] - vs[oy][ox + j - 1];
-                g[c][j] = s;
-            }
-        }
-        __syncthreads();
+        double s = 0;
+        for (int k = -MS_R; k <= MS_R; k++) s += (double)__ldg(src + c * plane + (size_t)clampi(y0 + k, 0, h - 1) * w + gx);
+        vs[c] = s;
     }
-    const double scale = 1.0 / 225.0;
-    const int gy = ty0 + oy;
-    if (gy >= h) return;
+    const int hc = t / 14, hseg = t - hc * 14;                      // horizontal work item (t < 70)
+    const int ox = t - 8, gxo = sx0 + ox;                           // output column of this thread
+    const bool has_out = ox >= 0 && ox < MS_OUT && gxo < w;
+    const int tp = ms_pad(t), oxp = ms_pad(ox < 0 ? 0 : ox);
+    float nin[5], nout[5];
+    for (int y = y0; y < y_end; y++) {
+        // prefetch the rows that enter / leave the window for the NEXT output row
+        if (y + 1 < y_end) {
+            const size_t oi = (size_t)clampi(y + 1 + MS_R, 0, h - 1) * w + gx, oo = (size_t)clampi(y - MS_R, 0, h - 1) * w + gx;
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-        const int gx = tx0 + ox + j;
-        if (gx >= w) continue;
-        const double g11 = g[0][j] * scale, g12 = g[1][j] * scale, g22 = g[2][j] * scale;
-        const double h1 = g[3][j] * scale, h2 = g[4][j] * scale;
-        const double idet = 1.0 / (g11 * g22 - g12 * g12 + 1e-3);
-        float2 o;
-        o.x = (float)((g11 * h2 - g12 * h1) * idet);
-        o.y = (float)((g22 * h1 - g12 * h2) * idet);
-        flow[(size_t)pair * plane + (size_t)gy * w + gx] = o;
+            for (int c = 0; c < 5; c++) { nin[c] = __ldg(src + c * plane + oi); nout[c] = __ldg(src + c * plane + oo); }
+        }
+#pragma unroll
+        for (int c = 0; c < 5; c++) row[c][tp] = (float)vs[c];
+        __syncthreads();
+        if (t < 70) {
+            // taps of output o are tile columns o + 1 .. o + 15 (tile column = output + 8, radius 7)
+            const float *r = row[hc];
+            const int c0 = hseg * MS_SEG + 1;
+            double s = 0;
+#pragma unroll
+            for (int k = 0; k < 2 * MS_R + 1; k++) s += (double)r[ms_pad(c0 + k)];
+            hs[hc][ms_pad(hseg * MS_SEG)] = (float)s;
+#pragma unroll
+            for (int j = 1; j < MS_SEG; j++) {
+                s += (double)r[ms_pad(c0 + j + 2 * MS_R)] - (double)r[ms_pad(c0 + j - 1)];
+                hs[hc][ms_pad(hseg * MS_SEG + j)] = (float)s;
+            }
+        }
+        __syncthreads();
+        if (has_out) {
+            const double scale = 1.0 / 225.0;
+            const double g11 = hs[0][oxp] * scale, g12 = hs[1][oxp] * scale, g22 = hs[2][oxp] * scale;
+            const double h1 = hs[3][oxp] * scale, h2 = hs[4][oxp] * scale;
+            const double idet = 1.0 / (g11 * g22 - g12 * g12 + 1e-3);
+            float2 o;
+            o.x = (float)((g11 * h2 - g12 * h1) * idet);
+            o.y = (float)((g22 * h1 - g12 * h2) * idet);
+            flow[(size_t)pair * plane + (size_t)y * w + gxo] = o;
+        }
+        if (y + 1 < y_end) {
+#pragma unroll
+            for (int c = 0; c < 5; c++) vs[c] += (double)nin[c] - (double)nout[c];
+        }
     }
 }
 
@@ -417,6 +491,7 @@ int run_farneback(vqa_ctx *c, const uint8_t *gray, int npairs, int h, int w, dou
     VQA_BUF(c, flowB, float2, "fb.flowB", full * npairs);
     PolyConst pc;
     make_poly(pc);
+    static const int pe_f32 = getenv("VQA_PE_F32") ? atoi(getenv("VQA_PE_F32")) : 0;
     float2 *flow = flowA, *prev = flowB;
     int ph = 0, pw = 0;
     for (int k = levels; k >= 0; k--) {
@@ -429,11 +504,22 @@ int run_farneback(vqa_ctx *c, const uint8_t *gray, int npairs, int h, int w, dou
         GaussTaps taps;
         make_gauss(ksz, sigma, taps);
         const int mode = (lw == w && lh == h) ? 0 : ((w == 2 * lw && h == 2 * lh) ? 1 : 2);
-        dim3 gF(cdiv(lw, 32), cdiv(lh, 8), nf), gP(cdiv(lw, 32), cdiv(lh, 8), npairs);
-        VQA_BYTES(c, ((double)full + 4.0 * lw * lh) * nf);
-        VQA_LAUNCH(c, k_fb_pyramid, gF, 256, 0, gray, h, w, lh, lw, mode, taps, I);
+        dim3 gF(cdiv(lw, PY_TW), cdiv(lh, PY_TH), nf), gP(cdiv(lw, 32), cdiv(lh, 8), npairs);
+        {
+            // worst-case source region of a 32x8 output tile (+ Gaussian radius), for the dynamic smem size
+            const double sx = (double)w / lw, sy = (double)h / lh;
+            const int rwp = (((int)ceil(PY_TW * sx) + 2 * (ksz / 2) + 4) + 3) & ~3;
+            const int rhm = (int)ceil(PY_TH * sy) + 2 * (ksz / 2) + 4;
+            const size_t smem = (((size_t)rhm * rwp + 15) & ~(size_t)15) + (size_t)rhm * 2 * PY_TW * sizeof(float);
+            if (smem > 200 * 1024) return set_err(c, VQA_E_UNSUPPORTED, "farneback pyramid tile needs %zu B of shared memory", smem);
+            if (smem > 48 * 1024)
+                VQA_CUDA(c, cudaFuncSetAttribute(k_fb_pyramid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            VQA_BYTES(c, ((double)full + 4.0 * lw * lh) * nf);
+            VQA_LAUNCH(c, k_fb_pyramid, gF, PY_TW * PY_TH, smem, gray, h, w, lh, lw, mode, taps, I, rwp);
+        }
         VQA_BYTES(c, 24.0 * lw * lh * nf);
-        VQA_LAUNCH(c, k_fb_polyexp, dim3(cdiv(lw, PE_TW), cdiv(lh, PE_TH), nf), 256, 0, I, lh, lw, pc, R);
+        if (pe_f32) VQA_LAUNCH(c, k_fb_polyexp<float>, dim3(cdiv(lw, PE_TW), cdiv(lh, PE_TH), nf), 256, 0, I, lh, lw, pc, R);
+        else VQA_LAUNCH(c, k_fb_polyexp<double>, dim3(cdiv(lw, PE_TW), cdiv(lh, PE_TH), nf), 256, 0, I, lh, lw, pc, R);
         if (k == levels) {
             VQA_CUDA(c, cudaMemsetAsync(flow, 0, sizeof(float2) * (size_t)lw * lh * npairs, c->stream));
         } else {
@@ -444,7 +530,7 @@ int run_farneback(vqa_ctx *c, const uint8_t *gray, int npairs, int h, int w, dou
         VQA_LAUNCH(c, k_fb_matrices, gP, 256, 0, R, flow, lh, lw, M);
         for (int it = 0; it < 3; it++) {
             VQA_BYTES(c, 28.0 * lw * lh * npairs);
-            VQA_LAUNCH(c, k_fb_blur_solve, dim3(cdiv(lw, BS_TW), cdiv(lh, BS_TH), npairs), 256, 0, M, lh, lw, flow);
+            VQA_LAUNCH(c, k_fb_blur_solve, dim3(cdiv(lw, MS_OUT), cdiv(lh, MS_H), npairs), MS_W, 0, M, lh, lw, flow);
             if (it < 2) {
                 VQA_BYTES(c, 68.0 * lw * lh * npairs);
                 VQA_LAUNCH(c, k_fb_matrices, gP, 256, 0, R, flow, lh, lw, M);

@@ -4,13 +4,29 @@
 // Replaces the cv2.cvtColor / cv2.resize / cv2.calcHist / np.log2 calls of
 // complexity_metrics.py:327-328,358-359,386,404-414,430,455-473,490-493,530-531.
 // Roofline: HBM.  Algorithmic bytes per analysed frame (identity resize): read 3*H*W, write H*W.
+#include <stdlib.h>
+
 #include "vqa_common.cuh"
 
 namespace vqa {
 
 // One lane per distinct bin does the shared-memory atomic for all lanes that hit that bin.
+template <bool AGG = true>
 __device__ __forceinline__ void hist_add(unsigned *h, unsigned bin, bool valid, int lane)
 {
+    if (!AGG) {
+        // plain shared-memory atomics, except that a warp whose lanes all hit the same bin (flat
+        // areas) issues one add: on B200 this is ~10x faster than per-bin match.any aggregation
+        // for textured frames (profiles/r01_notes.md) and keeps the flat-frame worst case at 1 atomic.
+        const unsigned vm = __ballot_sync(0xffffffffu, valid);
+        const unsigned b0 = __shfl_sync(0xffffffffu, bin, __ffs(vm | 0x80000000u) - 1);
+        if (__all_sync(0xffffffffu, !valid || bin == b0)) {
+            if (vm && lane == __ffs(vm) - 1) atomicAdd(&h[bin], (unsigned)__popc(vm));
+        } else if (valid) {
+            atomicAdd(&h[bin], 1u);
+        }
+        return;
+    }
     unsigned key = valid ? bin : 0xffffffffu;
     unsigned peers = __match_any_sync(0xffffffffu, key);
     if (valid && (__ffs(peers) - 1) == lane) atomicAdd(&h[bin], (unsigned)__popc(peers));
@@ -21,7 +37,7 @@ constexpr int GH_WARPS = GH_THREADS / 32;
 
 // grid = (blocks_per_frame, n_frames).  Each thread converts groups of 16 pixels: three 128-bit
 // loads of interleaved BGR, one 128-bit store of gray.
-template <bool HIST>
+template <bool HIST, bool AGG>
 __global__ void __launch_bounds__(GH_THREADS)
 k_gray_hist(const uint8_t *__restrict__ bgr, size_t frame_stride, int P, uint8_t *__restrict__ gray,
             uint32_t *__restrict__ hist)
@@ -70,10 +86,10 @@ k_gray_hist(const uint8_t *__restrict__ bgr, size_t frame_stride, int P, uint8_t
             unsigned Y = gray_of(B, G, R);
             out[px >> 2] |= Y << ((px & 3) * 8);
             if (HIST) {
-                hist_add(wh, B, valid, lane);
-                hist_add(wh + 256, G, valid, lane);
-                hist_add(wh + 512, R, valid, lane);
-                hist_add(wh + 768, Y, valid, lane);
+                hist_add<AGG>(wh, B, valid, lane);
+                hist_add<AGG>(wh + 256, G, valid, lane);
+                hist_add<AGG>(wh + 512, R, valid, lane);
+                hist_add<AGG>(wh + 768, Y, valid, lane);
             }
         }
         if (valid) {
@@ -254,13 +270,15 @@ int run_gray_hist(vqa_ctx *c, const uint8_t *bgr, int n, int h, int w, size_t fr
     int bpf = cdiv(cdiv(P, 16), GH_THREADS * 8);
     if (bpf < 1) bpf = 1;
     dim3 grid(bpf, n);
+    static const int agg = getenv("VQA_HIST_AGG") ? atoi(getenv("VQA_HIST_AGG")) : 0;
     if (hist) {
         VQA_CUDA(c, cudaMemsetAsync(hist, 0, sizeof(uint32_t) * 1024 * (size_t)n, c->stream));
         VQA_BYTES(c, 4.0 * P * n);
-        VQA_LAUNCH(c, k_gray_hist<true>, grid, GH_THREADS, 0, bgr, frame_stride, P, gray, hist);
+        if (agg) VQA_LAUNCH(c, (k_gray_hist<true, true>), grid, GH_THREADS, 0, bgr, frame_stride, P, gray, hist);
+        else VQA_LAUNCH(c, (k_gray_hist<true, false>), grid, GH_THREADS, 0, bgr, frame_stride, P, gray, hist);
     } else {
         VQA_BYTES(c, 4.0 * P * n);
-        VQA_LAUNCH(c, k_gray_hist<false>, grid, GH_THREADS, 0, bgr, frame_stride, P, gray, hist);
+        VQA_LAUNCH(c, (k_gray_hist<false, false>), grid, GH_THREADS, 0, bgr, frame_stride, P, gray, hist);
     }
     return VQA_OK;
 }

@@ -1,0 +1,109 @@
+"""Frame-range sharding host logic on CPU: world_size-2 gloo run of the partial-sum reduce
+ with the oracle standing in for the per-frame kernels, plus shard-count invariance
+of the closed-form EWM coefficients."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from oracle import np_oracle as NO
+from oracle import ref_port as RP
+
+
+def _rows_from_oracle(clip, a, halo, rw, rh, dtype):
+    rows = np.zeros(len(clip), dtype=dtype)
+    prev = halo
+    for i, f in enumerate(clip):
+        rows["hist_entropy"][i] = RP.o_hist(f, rw, rh)
+        rows["color_entropy"][i] = RP.o_color(f, rw, rh)
+        rows["dct_energy"][i] = RP.o_dct(f, rw, rh)
+        rows["edge_count"][i] = RP.o_edge(f, rw, rh)
+        rows["orb_count"][i] = RP.o_orb(f)
+        if prev is not None:
+            rows["motion"][i] = RP.o_motion((f, prev))
+            rows["temporal_dct"][i] = RP.o_tdct(NO.dct_input(prev, rw, rh), NO.dct_input(f, rw, rh), rw, rh)
+        else:
+            rows["motion"][i] = rows["temporal_dct"][i] = np.nan
+        prev = f
+    return rows
+
+
+def _host_partial(x, offset, total, alpha):
+    import rtvqa_b200
+    from rtvqa_b200 import sharding as SH
+    c = SH.ewm_coefficients(total, alpha)
+    return float(np.dot(c[offset:offset + len(x)], x))
+
+
+def _worker(rank, world, port, clip, out_path):
+    import torch.distributed as dist
+    import rtvqa_b200
+    from rtvqa_b200 import _native as N
+    from rtvqa_b200 import sharding as SH
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    k = len(clip)
+    a, b = SH.shard_range(k, rank, world)
+    halo = clip[a - 1] if a > 0 else None
+    rows = _rows_from_oracle(clip[a:b], a, halo, 64, 64, N.FRAME_DTYPE)
+    partials = SH.local_partials(rows, a, k, 0.8, _host_partial)
+    ints = np.array([int(rows["edge_count"][max(1 - a, 0):].sum()), int(rows["orb_count"][max(1 - a, 0):].sum()), len(rows)], np.int64)
+    partials, ints = SH.reduce_partials(partials, ints)
+    ts = 1000.0 * np.arange(k) / 30.0
+    fps = [NO.process_frame_interval_for_parallel((x, y)) for x, y in zip(ts[:-1], ts[1:])]
+    res = SH.finalize(partials, k, NO.smoothed_mean(fps, 0.8))
+    if rank == 0:
+        np.save(out_path, np.array(list(res) + [float(v) for v in ints]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def test_two_rank_gloo_reduce_matches_single_pass(vqa, small_clip, golden, tmp_path):
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "res.npy")
+    clip = small_clip[:8]
+    mp.spawn(_worker, args=(2, _free_port(), clip, out), nprocs=2, join=True)
+    got = np.load(out)
+    # (1) shard-count invariance: the single-rank evaluation of the same rows, <= 1e-12 relative
+    from rtvqa_b200 import _native as N
+    from rtvqa_b200 import sharding as SH
+    rows = _rows_from_oracle(clip, 0, None, 64, 64, N.FRAME_DTYPE)
+    one = SH.finalize(SH.local_partials(rows, 0, len(clip), 0.8, _host_partial), len(clip), got[7])
+    np.testing.assert_allclose(got[:8], one, rtol=1e-12)
+    # (2) and it is the reference's number (rows carry float32 fields like the reference's np.float32 returns)
+    want = RP.average_scene_complexity(clip, 64, 64, frame_interval=1)
+    np.testing.assert_allclose(got[:8], want, rtol=1e-6)
+    edges = [RP.o_edge(f, 64, 64) for f in clip[1:]]
+    assert got[8] == sum(edges) and got[10] == len(clip)          # integer totals identical for any rank count
+
+
+@pytest.mark.parametrize("k,world", [(30, 1), (30, 2), (30, 4), (30, 8), (7, 8), (299, 8)])
+def test_shard_ranges_and_partial_sum_invariance(vqa, k, world):
+    from rtvqa_b200 import sharding as SH
+    ranges = [SH.shard_range(k, r, world) for r in range(world)]
+    assert ranges[0][0] == 0 and ranges[-1][1] == k
+    assert all(ranges[i][1] == ranges[i + 1][0] for i in range(world - 1))
+    assert max(b - a for a, b in ranges) - min(b - a for a, b in ranges) <= 1
+    x = np.random.default_rng(k).normal(size=k)
+    for alpha in (0.8, 0.3, 1.0):
+        c = SH.ewm_coefficients(k, alpha)
+        whole = float(np.dot(c, x))
+        assert whole == pytest.approx(NO.smoothed_mean(x, alpha), rel=1e-13)
+        parts = sum(float(np.dot(c[a:b], x[a:b])) for a, b in ranges)
+        assert parts == pytest.approx(whole, rel=1e-13)
+
+
+def test_empty_series_conventions(vqa):
+    from rtvqa_b200 import sharding as SH
+    res = SH.finalize(np.zeros(len(SH.SERIES)), 1, float("nan"))      # one sampled frame: nothing analysed
+    assert all(np.isnan(v) for v in res[:6]) and res[6] == 0.0 and np.isnan(res[7])
+    res = SH.finalize(np.ones(len(SH.SERIES)), 2, 3.0)                 # two frames: temporal DCT still empty -> 0.0
+    assert res[0] == 1.0 and res[6] == 0.0 and res[7] == 3.0

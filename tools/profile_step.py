@@ -1,0 +1,23 @@
+"""One hot-path step bracketed by cudaProfilerStart/Stop for `ncu --profile-from-start off`.
+usage: python tools/profile_step.py [frames] [height] [width]"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import rtvqa_b200
+from rtvqa_b200 import _native as N
+
+F = int(sys.argv[1]) if len(sys.argv) > 1 else 24
+H = int(sys.argv[2]) if len(sys.argv) > 2 else 1080
+W = int(sys.argv[3]) if len(sys.argv) > 3 else 1920
+ctx = N.Context(0)
+clip = torch.from_numpy(rtvqa_b200.synth.synth_clip(F, H, W, seed=0)).cuda()
+(ry, ru, rv), (dy, du, dv) = rtvqa_b200.synth.synth_yuv_pairs(4, H, W, seed=1)
+ctx.complexity_frames(clip, W, H)            # warm-up (allocations, tensor maps, basis)
+torch.cuda.synchronize()
+torch.cuda.profiler.start()
+rows = ctx.complexity_frames(clip, W, H)
+fr = ctx.psnr_ssim((dy, du, dv), (ry, ru, rv))
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
+print("ok", rows["motion"][1:4], fr["psnr_avg"][:2])
