@@ -332,9 +332,12 @@ def _resolve_device(device):
     return int(os.environ.get("LOCAL_RANK", "0"))
 
 
-def get_context(device: int | None = None) -> Context:
-    """Process-wide context cache keyed by (pid, device): one context (scratch arena, streams) per GPU."""
-    key = (os.getpid(), _resolve_device(device))
+def get_context(device: int | None = None, role: str = "complexity") -> Context:
+    """Process-wide context cache keyed by (pid, device, role): one context (scratch arena, streams)
+    per GPU and per half of the path.  The full-reference half (``role="fr"``) has its own context so
+    a caller may run PSNR/SSIM of one clip in a second thread while the complexity pass of the same
+    clip is in flight (its H2D copies then overlap the Farneback compute)."""
+    key = (os.getpid(), _resolve_device(device), role)
     with _ctx_lock:
         ctx = _contexts.get(key)
         if ctx is None:

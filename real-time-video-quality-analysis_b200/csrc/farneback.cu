@@ -142,6 +142,79 @@ k_fb_pyramid(const uint8_t *__restrict__ gray, int H, int W, int lh, int lw, int
     I[(size_t)frame * lh * lw + (size_t)y * lw + x] = out;
 }
 
+// Fast path of the two largest pyramid levels (3-tap Gaussian): MODE 0 = level 0 (same size),
+// MODE 1 = level 1 (exact 2x decimation = mean of the 2x2 block of blurred pixels).  A thread owns
+// 4 adjacent SOURCE columns: 32-bit shared loads of the uint8 tile, 4 (MODE 0) or 2 (MODE 1)
+// outputs written with one vector store.  Same evaluation order as the generic kernel.
+template <int MODE>
+__global__ void __launch_bounds__(256)
+k_fb_pyramid3(const uint8_t *__restrict__ gray, int H, int W, int lh, int lw, float ke, float kc, float *__restrict__ I)
+{
+    constexpr int SR = MODE == 0 ? 10 : 18, NR = MODE == 0 ? 3 : 4, TROWS = MODE == 0 ? 8 : 16;
+    __shared__ __align__(16) uint8_t tile[SR][144];                  // source columns sx0-4 .. sx0+131
+    const int frame = blockIdx.z, tid = threadIdx.x;
+    const uint8_t *img = gray + (size_t)frame * H * W;
+    const int sx0 = blockIdx.x * 128, sy0 = blockIdx.y * TROWS;
+    const bool w4 = (W & 3) == 0;
+    for (int i = tid; i < SR * 34; i += 256) {
+        const int ry = i / 34, wx = i - ry * 34;
+        const uint8_t *row = img + (size_t)reflect101(sy0 - 1 + ry, H) * W;
+        const int gx = sx0 - 4 + wx * 4;
+        uint32_t v;
+        if (w4 && gx >= 0 && gx + 4 <= W) v = __ldg(reinterpret_cast<const uint32_t *>(row + gx));
+        else {
+            v = 0;
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                const int x = gx + b;
+                const int xr = (x >= -1 && x <= W) ? reflect101(x, W) : clampi(x, 0, W - 1);   // only x = -1 / W are ever used
+                v |= (uint32_t)__ldg(row + xr) << (8 * b);
+            }
+        }
+        *reinterpret_cast<uint32_t *>(&tile[ry][wx * 4]) = v;
+    }
+    __syncthreads();
+    const int xq = tid & 31, ty = tid >> 5;
+    float hr[NR][4];
+#pragma unroll
+    for (int r = 0; r < NR; r++) {
+        const uint32_t *wp = reinterpret_cast<const uint32_t *>(&tile[(MODE == 0 ? ty : 2 * ty) + r][4 * xq]);
+        const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2];
+        const float b[6] = {(float)(w0 >> 24), (float)(w1 & 255u), (float)((w1 >> 8) & 255u), (float)((w1 >> 16) & 255u),
+                            (float)(w1 >> 24), (float)(w2 & 255u)};
+#pragma unroll
+        for (int j = 0; j < 4; j++) hr[r][j] = kc * b[j + 1] + ke * (b[j] + b[j + 2]);
+    }
+    if (MODE == 0) {
+        const int y = sy0 + ty, x = sx0 + 4 * xq;
+        if (y >= lh || x >= lw) return;
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) o[j] = kc * hr[1][j] + ke * (hr[0][j] + hr[2][j]);
+        float *dst = I + (size_t)frame * lh * lw + (size_t)y * lw + x;
+        if (w4 && x + 4 <= lw) *reinterpret_cast<float4 *>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+        else
+            for (int j = 0; j < 4; j++)
+                if (x + j < lw) dst[j] = o[j];
+    } else {
+        const int y = sy0 / 2 + ty, x = sx0 / 2 + 2 * xq;
+        if (y >= lh || x >= lw) return;
+        float b0[4], b1[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            b0[j] = kc * hr[1][j] + ke * (hr[0][j] + hr[2][j]);
+            b1[j] = kc * hr[2][j] + ke * (hr[1][j] + hr[3][j]);
+        }
+        const float o0 = (b0[0] + b0[1] + b1[0] + b1[1]) * 0.25f, o1 = (b0[2] + b0[3] + b1[2] + b1[3]) * 0.25f;
+        float *dst = I + (size_t)frame * lh * lw + (size_t)y * lw + x;
+        if ((lw & 1) == 0 && x + 2 <= lw) *reinterpret_cast<float2 *>(dst) = make_float2(o0, o1);
+        else {
+            dst[0] = o0;
+            if (x + 1 < lw) dst[1] = o1;
+        }
+    }
+}
+
 constexpr int PE_TW = 64, PE_TH = 16, PE_R = 5;
 constexpr int PE_P = 76;                         // tile pitch (64 + 2*5 = 74, padded so rows stay 16-byte aligned)
 
@@ -234,27 +307,24 @@ k_fb_polyexp(const float *__restrict__ I, int h, int w, PolyConst pc, float *__r
     }
 }
 
-// flow_k = 2 * resize_f32(flow_{k+1}) (INTER_LINEAR upscale, OpenCV float tap rules)
-__global__ void __launch_bounds__(256)
-k_fb_upsample(const float2 *__restrict__ prev, int ph, int pw, float2 *__restrict__ flow, int lh, int lw)
+// flow_k(x, y) = 2 * resize_f32(flow_{k+1}) (INTER_LINEAR upscale, OpenCV float tap rules).  The
+// up-sampled flow is consumed only by the first UpdateMatrices of a level (the box-blur solve then
+// rewrites the whole field), so it is evaluated on the fly there and never stored.
+__device__ __forceinline__ float2 fb_upsampled_flow(const float2 *__restrict__ p, int ph, int pw, int x, int y, int lh, int lw)
 {
-    const int pair = blockIdx.z;
-    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (x >= lw || y >= lh) return;
-    const float2 *p = prev + (size_t)pair * ph * pw;
     int x0, x1, y0, y1;
     float ax, ay;
     lin_tap_f32(x, pw, lw, false, x0, x1, ax);
     lin_tap_f32(y, ph, lh, true, y0, y1, ay);
     const float a0 = 1.f - ax, b0 = 1.f - ay;
-    const float2 p00 = p[(size_t)y0 * pw + x0], p01 = p[(size_t)y0 * pw + x1];
-    const float2 p10 = p[(size_t)y1 * pw + x0], p11 = p[(size_t)y1 * pw + x1];
+    const float2 p00 = __ldg(p + (size_t)y0 * pw + x0), p01 = __ldg(p + (size_t)y0 * pw + x1);
+    const float2 p10 = __ldg(p + (size_t)y1 * pw + x0), p11 = __ldg(p + (size_t)y1 * pw + x1);
     float2 o;
     o.x = __fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p00.x, a0), __fmul_rn(p01.x, ax)), b0),
                     __fmul_rn(__fadd_rn(__fmul_rn(p10.x, a0), __fmul_rn(p11.x, ax)), ay)) * 2.f;
     o.y = __fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p00.y, a0), __fmul_rn(p01.y, ax)), b0),
                     __fmul_rn(__fadd_rn(__fmul_rn(p10.y, a0), __fmul_rn(p11.y, ax)), ay)) * 2.f;
-    flow[(size_t)pair * lh * lw + (size_t)y * lw + x] = o;
+    return o;
 }
 
 // FarnebackUpdateMatrices for one pixel: returns the 5 entries of M
@@ -305,16 +375,23 @@ __device__ __forceinline__ void fb_matrix_at(const float *__restrict__ R0, const
     m[4] = r6 * r2 + r5 * r3;
 }
 
+// INIT 0: flow read from memory; 1: flow up-sampled from the previous (coarser) level; 2: zero flow
+template <int INIT>
 __global__ void __launch_bounds__(256)
-k_fb_matrices(const float *__restrict__ R, const float2 *__restrict__ flow, int h, int w, float *__restrict__ M)
+k_fb_matrices(const float *__restrict__ R, const float2 *__restrict__ flow, int h, int w, float *__restrict__ M,
+              const float2 *__restrict__ prev, int ph, int pw)
 {
     const int pair = blockIdx.z;
     const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
     if (x >= w || y >= h) return;
     const size_t plane = (size_t)h * w;
     const float *R0 = R + (size_t)pair * 5 * plane, *R1 = R0 + 5 * plane;
+    float2 f;
+    if (INIT == 0) f = flow[(size_t)pair * plane + (size_t)y * w + x];
+    else if (INIT == 1) f = fb_upsampled_flow(prev + (size_t)pair * ph * pw, ph, pw, x, y, h, w);
+    else f = make_float2(0.f, 0.f);
     float m[5];
-    fb_matrix_at(R0, R1, plane, x, y, h, w, flow[(size_t)pair * plane + (size_t)y * w + x], m);
+    fb_matrix_at(R0, R1, plane, x, y, h, w, f, m);
     float *dst = M + (size_t)pair * 5 * plane + (size_t)y * w + x;
 #pragma unroll
     for (int c = 0; c < 5; c++) dst[c * plane] = m[c];
@@ -337,8 +414,9 @@ constexpr int MS_ROWP = MS_W + MS_W / 8 + 1, MS_HSP = MS_OUT + MS_OUT / 8 + 1;
 __global__ void __launch_bounds__(MS_W)
 k_fb_blur_solve(const float *__restrict__ M, int h, int w, float2 *__restrict__ flow)
 {
-    __shared__ float row[5][MS_ROWP];
-    __shared__ float hs[5][MS_HSP];
+    // kept in double: float<->double conversions run on the quarter-rate XU pipe (profiles/r01_notes.md)
+    __shared__ double row[5][MS_ROWP];
+    __shared__ double hs[5][MS_HSP];
     const int pair = blockIdx.z, t = threadIdx.x;
     const size_t plane = (size_t)h * w;
     const float *src = M + (size_t)pair * 5 * plane;
@@ -347,52 +425,63 @@ k_fb_blur_solve(const float *__restrict__ M, int h, int w, float2 *__restrict__ 
     const int y_end = min(y0 + MS_H, h);
     double vs[5];
 #pragma unroll
-    for (int c = 0; c < 5; c++) {
-        double s = 0;
-        for (int k = -MS_R; k <= MS_R; k++) s += (double)__ldg(src + c * plane + (size_t)clampi(y0 + k, 0, h - 1) * w + gx);
-        vs[c] = s;
+    for (int c = 0; c < 5; c++) vs[c] = 0;
+    for (int k = -MS_R; k <= MS_R; k++) {
+        const float *p = src + (size_t)clampi(y0 + k, 0, h - 1) * w + gx;
+#pragma unroll
+        for (int c = 0; c < 5; c++) vs[c] += (double)__ldg(p + c * plane);
     }
     const int hc = t / 14, hseg = t - hc * 14;                      // horizontal work item (t < 70)
     const int ox = t - 8, gxo = sx0 + ox;                           // output column of this thread
     const bool has_out = ox >= 0 && ox < MS_OUT && gxo < w;
-    const int tp = ms_pad(t), oxp = ms_pad(ox < 0 ? 0 : ox);
+    // shared-memory cursors with compile-time offsets (pad: one extra word per 8 columns)
+    double *my_row = &row[0][ms_pad(t)];
+    const double *hin = &row[t < 70 ? hc : 0][ms_pad((t < 70 ? hseg : 0) * MS_SEG + 1)];   // taps of output o: columns o+1 .. o+15
+    double *hout = &hs[t < 70 ? hc : 0][ms_pad((t < 70 ? hseg : 0) * MS_SEG)];
+    const double *my_hs = &hs[0][ms_pad(has_out ? ox : 0)];
+    float2 *fout = flow + (size_t)pair * plane + (size_t)y0 * w + (has_out ? gxo : 0);
+    // rows entering (yi) / leaving (yo) the 15-row window when the output row advances to y+1
+    int yi = y0 + 1 + MS_R, yo = y0 - MS_R;
+    const float *pin = src + (size_t)clampi(yi, 0, h - 1) * w + gx, *pout = src + (size_t)clampi(yo, 0, h - 1) * w + gx;
     float nin[5], nout[5];
     for (int y = y0; y < y_end; y++) {
-        // prefetch the rows that enter / leave the window for the NEXT output row
-        if (y + 1 < y_end) {
-            const size_t oi = (size_t)clampi(y + 1 + MS_R, 0, h - 1) * w + gx, oo = (size_t)clampi(y - MS_R, 0, h - 1) * w + gx;
+        const bool more = y + 1 < y_end;
+        if (more) {
 #pragma unroll
-            for (int c = 0; c < 5; c++) { nin[c] = __ldg(src + c * plane + oi); nout[c] = __ldg(src + c * plane + oo); }
+            for (int c = 0; c < 5; c++) { nin[c] = __ldg(pin + c * plane); nout[c] = __ldg(pout + c * plane); }
+            pin += (yi >= 0 && yi < h - 1) ? w : 0;                  // replicate border: the pointer stops at rows 0 / h-1
+            pout += (yo >= 0 && yo < h - 1) ? w : 0;
+            yi++;
+            yo++;
         }
 #pragma unroll
-        for (int c = 0; c < 5; c++) row[c][tp] = (float)vs[c];
+        for (int c = 0; c < 5; c++) my_row[c * MS_ROWP] = vs[c];
         __syncthreads();
         if (t < 70) {
-            // taps of output o are tile columns o + 1 .. o + 15 (tile column = output + 8, radius 7)
-            const float *r = row[hc];
-            const int c0 = hseg * MS_SEG + 1;
+            // element k of the 22-column span sits at padded offset k + ((k + 1) >> 3) from `hin`
             double s = 0;
 #pragma unroll
-            for (int k = 0; k < 2 * MS_R + 1; k++) s += (double)r[ms_pad(c0 + k)];
-            hs[hc][ms_pad(hseg * MS_SEG)] = (float)s;
+            for (int k = 0; k < 2 * MS_R + 1; k++) s += hin[k + ((k + 1) >> 3)];
+            hout[0] = s;
 #pragma unroll
             for (int j = 1; j < MS_SEG; j++) {
-                s += (double)r[ms_pad(c0 + j + 2 * MS_R)] - (double)r[ms_pad(c0 + j - 1)];
-                hs[hc][ms_pad(hseg * MS_SEG + j)] = (float)s;
+                s += hin[(j + 2 * MS_R) + ((j + 2 * MS_R + 1) >> 3)] - hin[(j - 1) + (j >> 3)];
+                hout[j] = s;
             }
         }
         __syncthreads();
         if (has_out) {
             const double scale = 1.0 / 225.0;
-            const double g11 = hs[0][oxp] * scale, g12 = hs[1][oxp] * scale, g22 = hs[2][oxp] * scale;
-            const double h1 = hs[3][oxp] * scale, h2 = hs[4][oxp] * scale;
+            const double g11 = my_hs[0] * scale, g12 = my_hs[MS_HSP] * scale, g22 = my_hs[2 * MS_HSP] * scale;
+            const double h1 = my_hs[3 * MS_HSP] * scale, h2 = my_hs[4 * MS_HSP] * scale;
             const double idet = 1.0 / (g11 * g22 - g12 * g12 + 1e-3);
             float2 o;
             o.x = (float)((g11 * h2 - g12 * h1) * idet);
             o.y = (float)((g22 * h1 - g12 * h2) * idet);
-            flow[(size_t)pair * plane + (size_t)y * w + gxo] = o;
+            *fout = o;
         }
-        if (y + 1 < y_end) {
+        fout += w;
+        if (more) {
 #pragma unroll
             for (int c = 0; c < 5; c++) vs[c] += (double)nin[c] - (double)nout[c];
         }
@@ -491,7 +580,7 @@ int run_farneback(vqa_ctx *c, const uint8_t *gray, int npairs, int h, int w, dou
     VQA_BUF(c, flowB, float2, "fb.flowB", full * npairs);
     PolyConst pc;
     make_poly(pc);
-    static const int pe_f32 = getenv("VQA_PE_F32") ? atoi(getenv("VQA_PE_F32")) : 0;
+    static const int pe_f32 = getenv("VQA_PE_F32") ? atoi(getenv("VQA_PE_F32")) : 1;
     float2 *flow = flowA, *prev = flowB;
     int ph = 0, pw = 0;
     for (int k = levels; k >= 0; k--) {
@@ -515,25 +604,30 @@ int run_farneback(vqa_ctx *c, const uint8_t *gray, int npairs, int h, int w, dou
             if (smem > 48 * 1024)
                 VQA_CUDA(c, cudaFuncSetAttribute(k_fb_pyramid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             VQA_BYTES(c, ((double)full + 4.0 * lw * lh) * nf);
-            VQA_LAUNCH(c, k_fb_pyramid, gF, PY_TW * PY_TH, smem, gray, h, w, lh, lw, mode, taps, I, rwp);
+            if (ksz == 3 && mode == 0) {
+                VQA_LAUNCH(c, k_fb_pyramid3<0>, dim3(cdiv(w, 128), cdiv(h, 8), nf), 256, 0, gray, h, w, lh, lw, taps.k[0], taps.k[1], I);
+            } else if (ksz == 3 && mode == 1) {
+                VQA_LAUNCH(c, k_fb_pyramid3<1>, dim3(cdiv(w, 128), cdiv(h, 16), nf), 256, 0, gray, h, w, lh, lw, taps.k[0], taps.k[1], I);
+            } else {
+                VQA_LAUNCH(c, k_fb_pyramid, gF, PY_TW * PY_TH, smem, gray, h, w, lh, lw, mode, taps, I, rwp);
+            }
         }
         VQA_BYTES(c, 24.0 * lw * lh * nf);
         if (pe_f32) VQA_LAUNCH(c, k_fb_polyexp<float>, dim3(cdiv(lw, PE_TW), cdiv(lh, PE_TH), nf), 256, 0, I, lh, lw, pc, R);
         else VQA_LAUNCH(c, k_fb_polyexp<double>, dim3(cdiv(lw, PE_TW), cdiv(lh, PE_TH), nf), 256, 0, I, lh, lw, pc, R);
         if (k == levels) {
-            VQA_CUDA(c, cudaMemsetAsync(flow, 0, sizeof(float2) * (size_t)lw * lh * npairs, c->stream));
+            VQA_BYTES(c, 60.0 * lw * lh * npairs);
+            VQA_LAUNCH(c, k_fb_matrices<2>, gP, 256, 0, R, flow, lh, lw, M, prev, ph, pw);
         } else {
-            VQA_BYTES(c, (8.0 * lw * lh + 8.0 * pw * ph) * npairs);
-            VQA_LAUNCH(c, k_fb_upsample, gP, 256, 0, prev, ph, pw, flow, lh, lw);
+            VQA_BYTES(c, (60.0 * lw * lh + 8.0 * pw * ph) * npairs);
+            VQA_LAUNCH(c, k_fb_matrices<1>, gP, 256, 0, R, flow, lh, lw, M, prev, ph, pw);
         }
-        VQA_BYTES(c, 68.0 * lw * lh * npairs);
-        VQA_LAUNCH(c, k_fb_matrices, gP, 256, 0, R, flow, lh, lw, M);
         for (int it = 0; it < 3; it++) {
             VQA_BYTES(c, 28.0 * lw * lh * npairs);
             VQA_LAUNCH(c, k_fb_blur_solve, dim3(cdiv(lw, MS_OUT), cdiv(lh, MS_H), npairs), MS_W, 0, M, lh, lw, flow);
             if (it < 2) {
                 VQA_BYTES(c, 68.0 * lw * lh * npairs);
-                VQA_LAUNCH(c, k_fb_matrices, gP, 256, 0, R, flow, lh, lw, M);
+                VQA_LAUNCH(c, k_fb_matrices<0>, gP, 256, 0, R, flow, lh, lw, M, prev, ph, pw);
             }
         }
         float2 *t = prev; prev = flow; flow = t;

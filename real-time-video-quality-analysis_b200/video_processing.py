@@ -138,7 +138,7 @@ def psnr_ssim_frames(main_planes, ref_planes, device=None):
     """Per-frame PSNR/SSIM of planar 8-bit stacks ((Y,U,V), each [n,h_c,w_c]); ``main`` is the
     distorted input [0:v], ``ref`` the reference [1:v] as in the reference's filter graph.
     Returns the structured array of ``_native.FR_DTYPE``."""
-    return N.get_context(device).psnr_ssim(main_planes, ref_planes)
+    return N.get_context(device, role="fr").psnr_ssim(main_planes, ref_planes)
 
 
 def _fmt_psnr(v):
