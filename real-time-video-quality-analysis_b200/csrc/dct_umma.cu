@@ -334,18 +334,48 @@ __global__ void k_dct_basis_split(int n, __nv_bfloat16 *__restrict__ hi, __nv_bf
     }
 }
 
-// uint8 [n][h][w] -> bf16 [n][h][ld]   (integers <= 255 are exact in bf16)
+// Per-frame integer mean m = round(sum x / (h w)).  The contraction runs on x - m (still exact
+// integers in bf16): every coefficient except DC is unchanged, and the DC path -- thousands of
+// same-sign products whose truncating fp32 tensor-core accumulation biased the energy by 7.6e-5 at
+// 4K -- now sums small mixed-sign terms.  k_dc_fix adds m * sqrt(h w) back afterwards.
 __global__ void __launch_bounds__(256)
-k_u8_to_bf16(const uint8_t *__restrict__ x, int h, int w, int ld, __nv_bfloat16 *__restrict__ y)
+k_frame_sum(const uint8_t *__restrict__ x, long per_frame, unsigned long long *__restrict__ sums)
+{
+    const int frame = blockIdx.y;
+    const uint8_t *p = x + (size_t)frame * per_frame;
+    unsigned long long acc = 0;
+    for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < per_frame; i += (long)gridDim.x * 256) acc += p[i];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(&sums[frame], acc);
+}
+
+// uint8 [n][h][w] -> bf16 [n][h][ld] of (x - mean)   (integers in [-255, 255] are exact in bf16)
+__global__ void __launch_bounds__(256)
+k_u8_to_bf16(const uint8_t *__restrict__ x, int h, int w, int ld, const unsigned long long *__restrict__ sums,
+             __nv_bfloat16 *__restrict__ y)
 {
     const int frame = blockIdx.y;
     const uint8_t *s = x + (size_t)frame * h * w;
     __nv_bfloat16 *d = y + (size_t)frame * h * ld;
     const long total = (long)h * w;
+    const int m = (int)((sums[frame] + (unsigned long long)(total / 2)) / (unsigned long long)total);
     for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
         const int r = (int)(i / w), c = (int)(i - (long)r * w);
-        d[(size_t)r * ld + c] = __float2bfloat16_rn((float)s[i]);
+        d[(size_t)r * ld + c] = __float2bfloat16_rn((float)((int)s[i] - m));
     }
+}
+
+__global__ void k_dc_fix(float *__restrict__ coef, size_t frame_stride, int h, int w, int n,
+                         const unsigned long long *__restrict__ sums, double *__restrict__ energy)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n) return;
+    const long total = (long)h * w;
+    const int m = (int)((sums[f] + (unsigned long long)(total / 2)) / (unsigned long long)total);
+    const double c_old = (double)coef[(size_t)f * frame_stride];
+    const float c_new = (float)(c_old + (double)m * sqrt((double)total));
+    coef[(size_t)f * frame_stride] = c_new;
+    energy[f] += (double)c_new * (double)c_new - c_old * c_old;
 }
 
 // ------------------------------------------------------------------------------- host side
@@ -426,9 +456,14 @@ int run_dct_umma(vqa_ctx *c, const uint8_t *x, int n, int h, int w, float *coef,
         VQA_CUDA(c, cudaFuncSetAttribute(k_dct_umma<BN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<BN, 2>::SMEM_BYTES));
         s->attr_set = true;
     }
+    VQA_BUF(c, sums, unsigned long long, "umma.sums", n);
+    VQA_CUDA(c, cudaMemsetAsync(sums, 0, sizeof(unsigned long long) * (size_t)n, c->stream));
     int bpf = cdiv((long)h * w, 256 * 8);
+    if (bpf < 1) bpf = 1;
+    VQA_BYTES(c, 1.0 * h * w * n);
+    VQA_LAUNCH(c, k_frame_sum, dim3(bpf, n), 256, 0, x, (long)h * w, sums);
     VQA_BYTES(c, 3.0 * h * w * n);
-    VQA_LAUNCH(c, k_u8_to_bf16, dim3(bpf < 1 ? 1 : bpf, n), 256, 0, x, h, w, ldw, X);
+    VQA_LAUNCH(c, k_u8_to_bf16, dim3(bpf, n), 256, 0, x, h, w, ldw, sums, X);
 
     alignas(64) CUtensorMap mA0, mA1, mB0, mB1;
     // GEMM 1: T^T[w x h] = Dw[w x w] * X^T ; A rows = w, K = w ; B = X rows = h, K = w, per frame
@@ -459,6 +494,7 @@ int run_dct_umma(vqa_ctx *c, const uint8_t *x, int n, int h, int w, float *coef,
         VQA_FLOPS(c, 3.0 * 2.0 * h * h * w * n);
         VQA_LAUNCH(c, (k_dct_umma<BN, 2>), grid, UM_THREADS, (UmmaCfg<BN, 2>::SMEM_BYTES), mA0, mA1, mB0, mB1, h, w, h, n, o2);
     }
+    VQA_LAUNCH(c, k_dc_fix, cdiv(n, 128), 128, 0, coef, (size_t)h * w, h, w, n, sums, energy);
     return VQA_OK;
 }
 

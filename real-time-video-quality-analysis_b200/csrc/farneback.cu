@@ -39,7 +39,11 @@ __device__ __forceinline__ int reflect101(int p, int n)
 
 __device__ __forceinline__ void lin_tap_f32(int d, int sn, int dn, bool vertical, int &i0, int &i1, float &a)
 {
-    const double scale = (double)sn / (double)dn;
+    // sn/dn is an exact power of two for every pyramid level of an image whose sides divide by 8;
+    // the reciprocal-multiply form below is then bit-identical to the division and avoids the
+    // ~30-instruction double division per call
+    const double scale = (sn == 2 * dn) ? 2.0 : (2 * sn == dn) ? 0.5 : (sn == 4 * dn) ? 4.0 : (sn == 8 * dn) ? 8.0
+                                                                                                  : (double)sn / (double)dn;
     float f = (float)(((double)d + 0.5) * scale - 0.5);
     int i = (int)floorf(f);
     a = f - (float)i;
@@ -412,7 +416,7 @@ __device__ __forceinline__ int ms_pad(int i) { return i + (i >> 3); }
 constexpr int MS_ROWP = MS_W + MS_W / 8 + 1, MS_HSP = MS_OUT + MS_OUT / 8 + 1;
 
 __global__ void __launch_bounds__(MS_W)
-k_fb_blur_solve(const float *__restrict__ M, int h, int w, float2 *__restrict__ flow)
+k_fb_blur_solve(const float *__restrict__ M, int h, int w, float2 *__restrict__ flow, int rows_per_block)
 {
     // kept in double: float<->double conversions run on the quarter-rate XU pipe (profiles/r01_notes.md)
     __shared__ double row[5][MS_ROWP];
@@ -420,9 +424,9 @@ k_fb_blur_solve(const float *__restrict__ M, int h, int w, float2 *__restrict__ 
     const int pair = blockIdx.z, t = threadIdx.x;
     const size_t plane = (size_t)h * w;
     const float *src = M + (size_t)pair * 5 * plane;
-    const int sx0 = blockIdx.x * MS_OUT, y0 = blockIdx.y * MS_H;
+    const int sx0 = blockIdx.x * MS_OUT, y0 = blockIdx.y * rows_per_block;
     const int gx = clampi(sx0 - 8 + t, 0, w - 1);
-    const int y_end = min(y0 + MS_H, h);
+    const int y_end = min(y0 + rows_per_block, h);
     double vs[5];
 #pragma unroll
     for (int c = 0; c < 5; c++) vs[c] = 0;
@@ -474,7 +478,11 @@ k_fb_blur_solve(const float *__restrict__ M, int h, int w, float2 *__restrict__ 
             const double scale = 1.0 / 225.0;
             const double g11 = my_hs[0] * scale, g12 = my_hs[MS_HSP] * scale, g22 = my_hs[2 * MS_HSP] * scale;
             const double h1 = my_hs[3 * MS_HSP] * scale, h2 = my_hs[4 * MS_HSP] * scale;
-            const double idet = 1.0 / (g11 * g22 - g12 * g12 + 1e-3);
+            // 1/det: float reciprocal seed + two Newton steps in double (relative error < 1e-15)
+            const double det = g11 * g22 - g12 * g12 + 1e-3;
+            double idet = (double)__frcp_rn((float)det);
+            idet = idet * (2.0 - det * idet);
+            idet = idet * (2.0 - det * idet);
             float2 o;
             o.x = (float)((g11 * h2 - g12 * h1) * idet);
             o.y = (float)((g22 * h1 - g12 * h2) * idet);
@@ -622,9 +630,19 @@ int run_farneback(vqa_ctx *c, const uint8_t *gray, int npairs, int h, int w, dou
             VQA_BYTES(c, (60.0 * lw * lh + 8.0 * pw * ph) * npairs);
             VQA_LAUNCH(c, k_fb_matrices<1>, gP, 256, 0, R, flow, lh, lw, M, prev, ph, pw);
         }
+        // rows per block of the marching blur: long strips amortise the 15-row warm-up, but the small
+        // pyramid levels need shorter strips to put >= ~3 waves of blocks on 148 SMs x 8 blocks
+        int rows_pb = MS_H;
+        {
+            const long want = 3L * c->sm_count * 8, per_row_strip = (long)cdiv(lw, MS_OUT) * npairs;
+            const long strips = (want + per_row_strip - 1) / per_row_strip;
+            if (strips > 0) rows_pb = (int)((lh + strips - 1) / strips);
+            if (rows_pb < 16) rows_pb = 16;
+            if (rows_pb > MS_H) rows_pb = MS_H;
+        }
         for (int it = 0; it < 3; it++) {
             VQA_BYTES(c, 28.0 * lw * lh * npairs);
-            VQA_LAUNCH(c, k_fb_blur_solve, dim3(cdiv(lw, MS_OUT), cdiv(lh, MS_H), npairs), MS_W, 0, M, lh, lw, flow);
+            VQA_LAUNCH(c, k_fb_blur_solve, dim3(cdiv(lw, MS_OUT), cdiv(lh, rows_pb), npairs), MS_W, 0, M, lh, lw, flow, rows_pb);
             if (it < 2) {
                 VQA_BYTES(c, 68.0 * lw * lh * npairs);
                 VQA_LAUNCH(c, k_fb_matrices<0>, gP, 256, 0, R, flow, lh, lw, M, prev, ph, pw);

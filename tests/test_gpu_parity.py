@@ -151,6 +151,25 @@ def test_rows_vs_reference_golden_mid_and_hd(ctx, golden, synth):
     _check_rows(ctx.complexity_frames(hd, 1920, 1080), golden["hd_native"], 3)
 
 
+def test_4k_rows_vs_oracle(ctx, synth):
+    """BASELINE.json config 4 shape (3840x2160): 3 frames against the CPU oracle."""
+    clip = synth.synth_clip(3, 2160, 3840, seed=2)
+    rows = ctx.complexity_frames(clip, 3840, 2160)
+    for i, f in enumerate(clip):
+        assert int(rows["edge_count"][i]) == int(RP.o_edge(f, 3840, 2160))
+        assert int(rows["orb_count"][i]) == RP.o_orb(f)
+        assert float(rows["hist_entropy"][i]) == pytest.approx(float(RP.o_hist(f, 3840, 2160)), rel=2e-6)
+        assert float(rows["color_entropy"][i]) == pytest.approx(float(RP.o_color(f, 3840, 2160)), rel=2e-6)
+        # Parseval: the exact integer energy is the DCT energy
+        assert float(rows["dct_energy"][i]) == pytest.approx(float(rows["gray_sq_sum"][i]), rel=3e-5)
+        assert int(rows["gray_sq_sum"][i]) == int(np.sum(NO.bgr2gray(f).astype(np.int64) ** 2))
+    for i in (1, 2):
+        assert float(rows["motion"][i]) == pytest.approx(float(RP.o_motion((clip[i], clip[i - 1]))), rel=RTOL)
+    g1, g2 = NO.bgr2gray(clip[1]), NO.bgr2gray(clip[2])
+    want = np.abs(NO.dct2(g1) - NO.dct2(g2)).sum()
+    assert float(rows["temporal_dct"][2]) == pytest.approx(want, rel=RTOL)
+
+
 def test_halo_and_chunking_invariance(ctx, small_clip, monkeypatch):
     """Shard-count invariance: splitting the clip into ranges with a one-frame halo,
     or into device chunks of any size, reproduces the single-pass rows exactly."""
