@@ -230,16 +230,10 @@ def run_b200(args):
     dist_np = [p.numpy() for p in dist_host]
     ref_np = [p.numpy() for p in ref_host]
 
-    from concurrent.futures import ThreadPoolExecutor
-    pool = ThreadPoolExecutor(max_workers=1)
-
     def step_e2e():
-        """Public API with HOST buffers: the H2D copies and the D2H of the rows are inside.  The
-        full-reference half runs in a second thread on its own context so that its 1.9 GB of H2D
-        overlaps the complexity pass (both calls release the GIL inside the C ABI)."""
-        fut = pool.submit(vp.psnr_ssim_frames, dist_np, ref_np, local)
-        rows = cm._clip_metrics(clip_np, W, H)
-        fr = fut.result()
+        """Public API with HOST buffers: the H2D copies and the D2H of the rows are inside.
+        video_processing.analyze_frames = both halves with one interleaved upload schedule."""
+        rows, fr = vp.analyze_frames(clip_np, W, H, dist_np, ref_np, local)
         vals = [cm._smoothed_mean(rows[name][SH.FIRST[name]:], alpha) for name in SH.SERIES]
         return vals, fr
 
@@ -343,7 +337,7 @@ def run_b200(args):
                        "l2": f"inputs ({(clip_np.nbytes + 2 * sum(p.nbytes for p in ref_np)) / 1e6:.0f} MB/step) larger than the 126 MB L2; no flush",
                        "parallelism": f"frame-range x{world}, one-frame halo over NCCL P2P, one all-reduce of partial sums"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "steps": e2e_steps, "api": "complexity_metrics._clip_metrics || video_processing.psnr_ssim_frames (2 threads) on pinned host arrays"},
+                    "steps": e2e_steps, "api": "video_processing.analyze_frames (vqa_analyze_clip) on pinned host arrays"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roofline,

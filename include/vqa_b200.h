@@ -124,6 +124,17 @@ VQA_API int vqa_psnr_ssim_planar(vqa_ctx *ctx, const uint8_t *const main_planes[
                          const int32_t plane_w[3], const int32_t plane_h[3], const int32_t stride[3],
                          int n, int on_device, vqa_fr_metrics *out);
 
+/* ---- a1-a8 + a13 for one clip with HOST buffers: what process_video_and_extract_metrics does per
+ * clip (video_processing.py:216 run_ffmpeg_metrics, :242 calculate_average_scene_complexity), as one
+ * call with one interleaved upload schedule -- the planes of the full-reference half ride the copy
+ * stream between the complexity chunks, so their transfer hides behind the Farneback compute.
+ * Results are identical to calling vqa_complexity_frames and vqa_psnr_ssim_planar in turn. */
+VQA_API int vqa_analyze_clip(vqa_ctx *ctx, const uint8_t *bgr, int n, int h, int w, size_t frame_stride,
+                             const vqa_cfg *cfg, vqa_frame_metrics *rows_out,
+                             const uint8_t *const main_planes[3], const uint8_t *const ref_planes[3],
+                             const int32_t plane_w[3], const int32_t plane_h[3], const int32_t stride[3],
+                             int n_pairs, vqa_fr_metrics *fr_out);
+
 /* ---- a9/a10: framerate variation + EWM-smoothed mean ----------------------------------------
  * vqa_framerate_series: process_frame_interval_for_parallel over consecutive timestamps
  * (complexity_metrics.py:150-165, driven at :296-298): fps[k] = 1000/(t[k+1]-t[k]) or 0.

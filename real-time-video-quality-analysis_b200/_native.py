@@ -21,7 +21,7 @@ M_ALL = 0x7F
 EXPORTS = [
     "vqa_abi_version", "vqa_init", "vqa_destroy", "vqa_last_error", "vqa_set_stream", "vqa_sync",
     "vqa_kernel_launches", "vqa_stage_ms", "vqa_reset_timers", "vqa_complexity_frames",
-    "vqa_psnr_ssim_planar", "vqa_framerate_series", "vqa_ewm_partial", "vqa_debug_gray",
+    "vqa_psnr_ssim_planar", "vqa_analyze_clip", "vqa_framerate_series", "vqa_ewm_partial", "vqa_debug_gray",
     "vqa_debug_resize", "vqa_debug_hist", "vqa_debug_orb", "vqa_kernel_profile", "vqa_kernel_report", "vqa_debug_canny", "vqa_debug_flow", "vqa_debug_dct",
 ]
 
@@ -73,6 +73,8 @@ def load_library():
         L.vqa_complexity_frames.argtypes = [vp, u8p, C.c_int, C.c_int, C.c_int, C.c_size_t, u8p, C.c_int,
                                             C.POINTER(Cfg), vp]
         L.vqa_psnr_ssim_planar.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), i32p, i32p, i32p, C.c_int, C.c_int, vp]
+        L.vqa_analyze_clip.argtypes = [vp, u8p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.POINTER(Cfg), vp,
+                                       C.POINTER(vp), C.POINTER(vp), i32p, i32p, i32p, C.c_int, vp]
         L.vqa_framerate_series.argtypes = [vp, vp, C.c_int, vp]
         L.vqa_ewm_partial.argtypes = [vp, vp, C.c_int, C.c_int64, C.c_int64, C.c_double, f64p]
         L.vqa_debug_gray.argtypes = [vp, u8p, C.c_int, C.c_int, u8p]
@@ -237,6 +239,36 @@ class Context:
         self._check(rc, "vqa_psnr_ssim_planar")
         del keep
         return out
+
+    def analyze_clip(self, frames, resize_width, resize_height, main_planes, ref_planes, mask=M_ALL, dct_impl=0):
+        """Host-buffer fast path for one clip: complexity rows + PSNR/SSIM rows with one interleaved
+        upload schedule (vqa_analyze_clip).  frames (n,h,w,3) uint8; planes 3 x [n_pairs,h_c,w_c] uint8."""
+        frames = _np_u8(frames)
+        if frames.ndim != 4 or frames.shape[-1] != 3:
+            raise TypeError("expected (n,h,w,3) uint8 BGR frames")
+        n, h, w, _ = frames.shape
+        keep, mp, rp = [], (C.c_void_p * 3)(), (C.c_void_p * 3)()
+        pw, ph, st = (C.c_int32 * 3)(), (C.c_int32 * 3)(), (C.c_int32 * 3)()
+        npairs = None
+        for i in range(3):
+            a, b = _np_u8(main_planes[i]), _np_u8(ref_planes[i])
+            if a.ndim != 3 or a.shape != b.shape:
+                raise TypeError("planes must be [n_pairs,h_c,w_c] and main/ref must agree")
+            npairs = a.shape[0] if npairs is None else npairs
+            if a.shape[0] != npairs:
+                raise TypeError("planes disagree on the pair count")
+            mp[i], rp[i], ph[i], pw[i], st[i] = a.ctypes.data, b.ctypes.data, a.shape[1], a.shape[2], a.shape[2]
+            keep += [a, b]
+        rows = np.zeros(n, dtype=FRAME_DTYPE)
+        fr = np.zeros(npairs, dtype=FR_DTYPE)
+        cfg = Cfg(int(resize_width), int(resize_height), int(mask), int(dct_impl))
+        with self.lock:
+            rc = self.lib.vqa_analyze_clip(self.h, C.c_void_p(frames.ctypes.data), n, h, w, h * w * 3, C.byref(cfg),
+                                           C.c_void_p(rows.ctypes.data), mp, rp, pw, ph, st, npairs,
+                                           C.c_void_p(fr.ctypes.data))
+        self._check(rc, "vqa_analyze_clip")
+        del keep
+        return rows, fr
 
     # ------------------------------------------------------------------ a9 / a10
     def framerate_series(self, timestamps_ms):

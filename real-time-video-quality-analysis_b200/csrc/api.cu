@@ -77,6 +77,13 @@ void stage_begin(vqa_ctx *c, const char *stage)
     cudaEventRecord(t.ev[t.used].first, c->stream);
 }
 
+cudaError_t wait_stream(vqa_ctx *c)
+{
+    cudaError_t e = cudaEventRecord(c->ev_sync, c->stream);
+    if (e != cudaSuccess) return e;
+    return cudaEventSynchronize(c->ev_sync);
+}
+
 void stage_end(vqa_ctx *c, const char *stage)
 {
     if (!c->timing) return;
@@ -118,10 +125,13 @@ int vqa_init(int device, vqa_ctx **out)
         return set_err(nullptr, VQA_E_CUDA, "stream creation failed");
     }
     c->own_stream = true;
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < 3; i++) {
         cudaEventCreateWithFlags(&c->ev_copy[i], cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming);
+        // host waits on these must yield, not spin: a spinning waiter in a second thread (the FR half)
+        // slowed the kernel-launching thread of the complexity half enough to serialise the two
+        cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming | cudaEventBlockingSync);
     }
+    cudaEventCreateWithFlags(&c->ev_sync, cudaEventDisableTiming | cudaEventBlockingSync);
     *out = c;
     return VQA_OK;
 }
@@ -137,7 +147,8 @@ void vqa_destroy(vqa_ctx *c)
     for (auto &kv : c->pinned) if (kv.second.p) cudaFreeHost(kv.second.p);
     for (auto &kv : c->timers) for (auto &p : kv.second.ev) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     for (auto &kv : c->krec) for (auto &p : kv.second.ev) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
-    for (int i = 0; i < 2; i++) { cudaEventDestroy(c->ev_copy[i]); cudaEventDestroy(c->ev_done[i]); }
+    for (int i = 0; i < 3; i++) { cudaEventDestroy(c->ev_copy[i]); cudaEventDestroy(c->ev_done[i]); }
+    cudaEventDestroy(c->ev_sync);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     cudaStreamDestroy(c->copy_stream);
     delete c;
@@ -232,7 +243,7 @@ static int pick_chunk(vqa_ctx *c, int h, int w, int rw, int rh, unsigned mask)
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
     const double hw = (double)h * w, rr = (double)rw * rh;
-    double per = hw * 3 * 2 + hw * 2 + rr * 8;                         // input double buffer, gray, labels/state
+    double per = hw * 3 * 3 + hw * 2 + rr * 8;                         // input double buffer, gray, labels/state
     if (mask & VQA_M_MOTION) per += hw * 66;                           // I, R, M, 2 x flow
     if (mask & (VQA_M_DCT | VQA_M_TDCT)) per += rr * 16;               // X, T (hi/lo), C
     // scratch already held by this context is reusable, so count it as free
@@ -243,8 +254,32 @@ static int pick_chunk(vqa_ctx *c, int h, int w, int rw, int rh, unsigned mask)
     return std::max(1, std::min(ch, 48));
 }
 
-int vqa_complexity_frames(vqa_ctx *c, const uint8_t *bgr, int n, int h, int w, size_t frame_stride,
-                          const uint8_t *halo, int on_device, const vqa_cfg *cfg, vqa_frame_metrics *out)
+}  // extern "C"
+
+namespace {
+// Extra host->device copies that ride the copy stream BETWEEN the complexity chunks (the planes of the
+// full-reference half in vqa_analyze_clip): one stream, deterministic order, chunk copies always first.
+struct SideCopy { uint8_t *dst; const uint8_t *src; size_t bytes, done; };
+struct SideLoad {
+    std::vector<SideCopy> copies;
+    size_t total = 0, issued = 0;
+};
+int side_issue(vqa_ctx *c, SideLoad *s, size_t budget)
+{
+    for (auto &cp : s->copies) {
+        while (budget > 0 && cp.done < cp.bytes) {
+            const size_t nb = std::min(budget, cp.bytes - cp.done);
+            VQA_CUDA(c, cudaMemcpyAsync(cp.dst + cp.done, cp.src + cp.done, nb, cudaMemcpyHostToDevice, c->copy_stream));
+            cp.done += nb;
+            s->issued += nb;
+            budget -= nb;
+        }
+    }
+    return VQA_OK;
+}
+
+int complexity_impl(vqa_ctx *c, const uint8_t *bgr, int n, int h, int w, size_t frame_stride, const uint8_t *halo,
+                    int on_device, const vqa_cfg *cfg, vqa_frame_metrics *out, SideLoad *side)
 {
     if (!c) return VQA_E_INVALID;
     if (!bgr || !cfg || !out || n < 0 || h <= 0 || w <= 0)
@@ -281,28 +316,33 @@ int vqa_complexity_frames(vqa_ctx *c, const uint8_t *bgr, int n, int h, int w, s
     }
     float *Cbuf = nullptr;
     if (want_dct) { VQA_BUF(c, cb_, float, "dct.coef", RR * (CH + 1)); Cbuf = cb_; }
-    uint8_t *in[2] = {nullptr, nullptr};
+    // Host input is staged through THREE device slots.  A copy is enqueued only once the slot is
+    // free (host-side event wait, which does not block in steady state because the slot was released
+    // two chunks ago): an event-gated copy parked at the head of the DMA queue would stall the
+    // copies of every other stream / context behind it (measured: the FR half ran slower in a
+    // second thread than sequentially).
+    uint8_t *in[3] = {nullptr, nullptr, nullptr};
     if (!on_device) {
         VQA_BUF(c, in0, uint8_t, "in.bgr0", FB * CH);
         VQA_BUF(c, in1, uint8_t, "in.bgr1", FB * CH);
-        in[0] = in0; in[1] = in1;
+        VQA_BUF(c, in2, uint8_t, "in.bgr2", FB * CH);
+        in[0] = in0; in[1] = in1; in[2] = in2;
     }
     const int nchunks = cdiv(n, CH);
     auto h2d_chunk = [&](int ci) -> int {
         const int s = ci * CH, m = std::min(CH, n - s);
         if (frame_stride == FB) {
-            VQA_CUDA(c, cudaMemcpyAsync(in[ci & 1], bgr + (size_t)s * frame_stride, FB * m, cudaMemcpyHostToDevice, c->copy_stream));
+            VQA_CUDA(c, cudaMemcpyAsync(in[ci % 3], bgr + (size_t)s * frame_stride, FB * m, cudaMemcpyHostToDevice, c->copy_stream));
         } else {
-            VQA_CUDA(c, cudaMemcpy2DAsync(in[ci & 1], FB, bgr + (size_t)s * frame_stride, frame_stride, FB, m,
+            VQA_CUDA(c, cudaMemcpy2DAsync(in[ci % 3], FB, bgr + (size_t)s * frame_stride, frame_stride, FB, m,
                                           cudaMemcpyHostToDevice, c->copy_stream));
         }
-        VQA_CUDA(c, cudaEventRecord(c->ev_copy[ci & 1], c->copy_stream));
+        VQA_CUDA(c, cudaEventRecord(c->ev_copy[ci % 3], c->copy_stream));
         return VQA_OK;
     };
     stage_begin(c, "all");
     if (!on_device) {
-        VQA_CUDA(c, cudaEventRecord(c->ev_done[0], c->stream));     // orders the copy stream after prior work
-        VQA_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_done[0], 0));
+        VQA_CUDA(c, cudaStreamSynchronize(c->stream));              // prior work may still read the staging slots
         int rc = h2d_chunk(0);
         if (rc) return rc;
     }
@@ -335,12 +375,14 @@ int vqa_complexity_frames(vqa_ctx *c, const uint8_t *bgr, int n, int h, int w, s
             src = bgr + (size_t)s * frame_stride;
             stride = frame_stride;
         } else {
-            VQA_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copy[ci & 1], 0));
+            VQA_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copy[ci % 3], 0));
             if (ci + 1 < nchunks) {
-                if (ci >= 1) VQA_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_done[(ci + 1) & 1], 0));
+                if (ci >= 2) VQA_CUDA(c, cudaEventSynchronize(c->ev_done[(ci + 1) % 3]));   // chunk ci-2 released the slot
                 if ((rc = h2d_chunk(ci + 1))) return rc;
             }
-            src = in[ci & 1];
+            if (side && nchunks > 0)                      // a slice of the side load behind the next chunk's copy
+                if ((rc = side_issue(c, side, side->total / nchunks + 1))) return rc;
+            src = in[ci % 3];
             stride = FB;
         }
         uint8_t *Gc = G + HW;                       // slots 1..m
@@ -394,10 +436,15 @@ int vqa_complexity_frames(vqa_ctx *c, const uint8_t *bgr, int n, int h, int w, s
         }
         if (want_motion || want_tdct)
             VQA_CUDA(c, cudaMemcpyAsync(G, G + (size_t)m * HW, HW, cudaMemcpyDeviceToDevice, c->stream));
-        if (!on_device) VQA_CUDA(c, cudaEventRecord(c->ev_done[ci & 1], c->stream));
+        if (!on_device) VQA_CUDA(c, cudaEventRecord(c->ev_done[ci % 3], c->stream));
         has_prev = true;
     }
     stage_end(c, "all");
+    if (side) {                                        // whatever is left, then make it visible to the compute stream
+        if ((rc = side_issue(c, side, side->total))) return rc;
+        VQA_CUDA(c, cudaEventRecord(c->ev_copy[0], c->copy_stream));
+        VQA_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copy[0], 0));
+    }
     // ---- results -> host
     struct Host {
         float *hent, *cent;
@@ -425,7 +472,7 @@ int vqa_complexity_frames(vqa_ctx *c, const uint8_t *bgr, int n, int h, int w, s
     if (want_motion) D2H(hr.mag, d_mag, double);
     if (want_orb) D2H(hr.orb, d_orb, int);
 #undef D2H
-    VQA_CUDA(c, cudaStreamSynchronize(c->stream));
+    VQA_CUDA(c, wait_stream(c));
     const float nanf_ = nanf("");
     for (int i = 0; i < n; i++) {
         vqa_frame_metrics &o = out[i];
@@ -440,6 +487,61 @@ int vqa_complexity_frames(vqa_ctx *c, const uint8_t *bgr, int n, int h, int w, s
         o.gray_sq_sum = want_dct ? hr.sq[i] : 0;
     }
     return VQA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int vqa_complexity_frames(vqa_ctx *c, const uint8_t *bgr, int n, int h, int w, size_t frame_stride,
+                          const uint8_t *halo, int on_device, const vqa_cfg *cfg, vqa_frame_metrics *out)
+{
+    return complexity_impl(c, bgr, n, h, w, frame_stride, halo, on_device, cfg, out, nullptr);
+}
+
+// Both halves of one clip with ONE interleaved upload schedule: the planes of the full-reference half
+// are sliced between the complexity chunks on the same copy stream, so their 2 x 1.5 HW bytes per
+// pair hide behind the Farneback compute instead of adding ~34 ms per 300 1080p pairs.
+int vqa_analyze_clip(vqa_ctx *c, const uint8_t *bgr, int n, int h, int w, size_t frame_stride, const vqa_cfg *cfg,
+                     vqa_frame_metrics *rows_out, const uint8_t *const main_planes[3],
+                     const uint8_t *const ref_planes[3], const int32_t plane_w[3], const int32_t plane_h[3],
+                     const int32_t stride[3], int n_pairs, vqa_fr_metrics *fr_out)
+{
+    if (!c) return VQA_E_INVALID;
+    if (!main_planes || !ref_planes || !plane_w || !plane_h || !stride || !fr_out || n_pairs <= 0 || n <= 0)
+        return set_err(c, VQA_E_INVALID, "vqa_analyze_clip: bad argument");
+    VQA_CUDA(c, cudaSetDevice(c->device));
+    size_t pb[3], tot = 0;
+    for (int p = 0; p < 3; p++) {
+        if (!main_planes[p] || !ref_planes[p] || plane_w[p] <= 0 || plane_h[p] <= 0 || stride[p] < plane_w[p])
+            return set_err(c, VQA_E_INVALID, "vqa_analyze_clip: bad plane %d", p);
+        pb[p] = (size_t)plane_h[p] * stride[p] * n_pairs;
+        tot += 2 * pb[p];
+    }
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    if (tot > free_b / 4) {                            // does not fit beside the complexity scratch: run the halves in turn
+        int rc = vqa_psnr_ssim_planar(c, main_planes, ref_planes, plane_w, plane_h, stride, n_pairs, 0, fr_out);
+        if (rc) return rc;
+        return complexity_impl(c, bgr, n, h, w, frame_stride, nullptr, 0, cfg, rows_out, nullptr);
+    }
+    VQA_BUF(c, dm, uint8_t, "fr.all_main", pb[0] + pb[1] + pb[2]);
+    VQA_BUF(c, dr, uint8_t, "fr.all_ref", pb[0] + pb[1] + pb[2]);
+    VQA_CUDA(c, cudaStreamSynchronize(c->stream));
+    SideLoad side;
+    const uint8_t *dmp[3], *drp[3];
+    size_t off = 0;
+    for (int p = 0; p < 3; p++) {
+        side.copies.push_back({dm + off, main_planes[p], pb[p], 0});
+        side.copies.push_back({dr + off, ref_planes[p], pb[p], 0});
+        dmp[p] = dm + off;
+        drp[p] = dr + off;
+        off += pb[p];
+    }
+    side.total = tot;
+    int rc = complexity_impl(c, bgr, n, h, w, frame_stride, nullptr, 0, cfg, rows_out, &side);
+    if (rc) return rc;
+    return vqa_psnr_ssim_planar(c, dmp, drp, plane_w, plane_h, stride, n_pairs, 1, fr_out);
 }
 
 int vqa_psnr_ssim_planar(vqa_ctx *c, const uint8_t *const main_planes[3], const uint8_t *const ref_planes[3],
@@ -459,7 +561,8 @@ int vqa_psnr_ssim_planar(vqa_ctx *c, const uint8_t *const main_planes[3], const 
     stage_begin(c, "frscore");
     size_t up_bytes = 0;
     for (int p = 0; p < 3; p++) up_bytes = std::max(up_bytes, (size_t)plane_h[p] * stride[p]);
-    const int CH = std::min(n, 64);
+    const char *fr_env = getenv("VQA_FR_CHUNK");
+    const int CH = std::min(n, (fr_env && atoi(fr_env) > 0) ? atoi(fr_env) : 64);
     uint8_t *buf[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
     if (!on_device) {
         VQA_BUF(c, a0, uint8_t, "fr.a0", up_bytes * CH);
@@ -470,8 +573,8 @@ int vqa_psnr_ssim_planar(vqa_ctx *c, const uint8_t *const main_planes[3], const 
     }
     int rc, slot = 0;
     if (!on_device) {
+        VQA_CUDA(c, cudaStreamSynchronize(c->stream));
         VQA_CUDA(c, cudaEventRecord(c->ev_done[0], c->stream));
-        VQA_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_done[0], 0));
         VQA_CUDA(c, cudaEventRecord(c->ev_done[1], c->stream));
     }
     for (int p = 0; p < 3; p++) {
@@ -481,7 +584,7 @@ int vqa_psnr_ssim_planar(vqa_ctx *c, const uint8_t *const main_planes[3], const 
             const uint8_t *a = main_planes[p] + (size_t)s * pb, *b = ref_planes[p] + (size_t)s * pb;
             if (!on_device) {
                 // copy on the copy stream once the kernel that last used this slot is done
-                VQA_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_done[slot], 0));
+                VQA_CUDA(c, cudaEventSynchronize(c->ev_done[slot]));     // never park a gated copy in the DMA queue
                 VQA_CUDA(c, cudaMemcpyAsync(buf[slot][0], a, pb * m, cudaMemcpyHostToDevice, c->copy_stream));
                 VQA_CUDA(c, cudaMemcpyAsync(buf[slot][1], b, pb * m, cudaMemcpyHostToDevice, c->copy_stream));
                 VQA_CUDA(c, cudaEventRecord(c->ev_copy[slot], c->copy_stream));
@@ -501,7 +604,7 @@ int vqa_psnr_ssim_planar(vqa_ctx *c, const uint8_t *const main_planes[3], const 
     double *h_ssim = (double *)(h_sse + 3 * (size_t)n);
     VQA_CUDA(c, cudaMemcpyAsync(h_sse, d_sse, sizeof(unsigned long long) * 3 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
     VQA_CUDA(c, cudaMemcpyAsync(h_ssim, d_ssim, sizeof(double) * 3 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
-    VQA_CUDA(c, cudaStreamSynchronize(c->stream));
+    VQA_CUDA(c, wait_stream(c));
     double area[3], tot = 0;
     for (int p = 0; p < 3; p++) { area[p] = (double)plane_w[p] * plane_h[p]; tot += area[p]; }
     for (int i = 0; i < n; i++) {

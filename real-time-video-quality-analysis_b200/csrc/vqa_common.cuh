@@ -46,8 +46,9 @@ struct vqa_ctx {
     std::map<std::string, vqa::Buf> pinned;       // named grow-only pinned host staging
     bool timing = false;
     std::map<std::string, vqa::StageTimer> timers;
-    cudaEvent_t ev_copy[2] = {nullptr, nullptr};
-    cudaEvent_t ev_done[2] = {nullptr, nullptr};
+    cudaEvent_t ev_copy[3] = {nullptr, nullptr, nullptr};   // H2D of staging slot s finished
+    cudaEvent_t ev_done[3] = {nullptr, nullptr, nullptr};   // compute that read staging slot s finished
+    cudaEvent_t ev_sync = nullptr;                          // blocking-sync event for end-of-call waits
     bool ktiming = false;                         // per-kernel CUDA-event timing (bench roofline leg)
     std::map<std::string, vqa::KRec> krec;
     double cur_bytes = 0, cur_flops = 0;          // algorithmic traffic of the NEXT launch
@@ -61,6 +62,7 @@ void *dev_buf(vqa_ctx *c, const char *name, size_t bytes);     // nullptr on fai
 void *pinned_buf(vqa_ctx *c, const char *name, size_t bytes);
 void stage_begin(vqa_ctx *c, const char *stage);
 void stage_end(vqa_ctx *c, const char *stage);
+cudaError_t wait_stream(vqa_ctx *c);                           // yielding wait for c->stream (no driver-lock spinning)
 
 #define VQA_CUDA(c, call)                                                                       \
     do {                                                                                        \

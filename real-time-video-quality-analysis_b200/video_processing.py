@@ -141,6 +141,15 @@ def psnr_ssim_frames(main_planes, ref_planes, device=None):
     return N.get_context(device, role="fr").psnr_ssim(main_planes, ref_planes)
 
 
+def analyze_frames(frames, resize_width, resize_height, main_planes, ref_planes, device=None):
+    """Both halves of ``process_video_and_extract_metrics`` (reference :216 PSNR/SSIM, :242 scene
+    complexity) for pre-decoded HOST buffers in one device pass with one interleaved upload schedule
+    (``vqa_analyze_clip``): ``frames`` (n,h,w,3) uint8 BGR sampled frames, planes 3 x [n_pairs,h_c,w_c]
+    uint8 (distorted = main, reference = ref).  Returns (complexity rows, PSNR/SSIM rows); identical to
+    ``complexity_metrics._clip_metrics`` + ``psnr_ssim_frames`` called in turn."""
+    return N.get_context(device).analyze_clip(frames, resize_width, resize_height, main_planes, ref_planes)
+
+
 def _fmt_psnr(v):
     return "inf" if np.isinf(v) else "%0.2f" % v
 

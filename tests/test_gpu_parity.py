@@ -195,6 +195,21 @@ def test_device_resident_input_matches_host_input(ctx, small_clip):
         assert np.array_equal(a[f], b[f], equal_nan=True), f
 
 
+def test_analyze_clip_equals_the_two_halves(ctx, synth, small_clip, monkeypatch):
+    """vqa_analyze_clip (interleaved upload schedule) returns exactly what the two calls return."""
+    (ry, ru, rv), (dy, du, dv) = synth.synth_yuv_pairs(len(small_clip), 96, 128, seed=7)
+    for chunk in (None, "5"):
+        if chunk:
+            monkeypatch.setenv("VQA_CHUNK", chunk)
+        rows, fr = ctx.analyze_clip(small_clip, 64, 64, (dy, du, dv), (ry, ru, rv))
+        a = ctx.complexity_frames(small_clip, 64, 64)
+        b = ctx.psnr_ssim((dy, du, dv), (ry, ru, rv))
+        for f in a.dtype.names:
+            assert np.array_equal(rows[f], a[f], equal_nan=True), f
+        for f in b.dtype.names:
+            assert np.array_equal(fr[f], b[f]), f
+
+
 def test_zero_and_constant_frames(ctx):
     z = np.zeros((2, 48, 64, 3), np.uint8)
     r = ctx.complexity_frames(z, 64, 64)
