@@ -415,34 +415,53 @@ constexpr int MS_W = 128, MS_OUT = 112, MS_R = 7, MS_H = 96, MS_SEG = 8;
 __device__ __forceinline__ int ms_pad(int i) { return i + (i >> 3); }
 constexpr int MS_ROWP = MS_W + MS_W / 8 + 1, MS_HSP = MS_OUT + MS_OUT / 8 + 1;
 
+// running sum kept as an unevaluated float pair (hi + lo): Knuth's TwoSum adds x exactly into hi and
+// the rounding error into lo, ~48 significant bits with FP32 adds only
+__device__ __forceinline__ void ff_add(float &hi, float &lo, float x)
+{
+    const float s = __fadd_rn(hi, x);
+    const float bb = __fsub_rn(s, hi);
+    const float e = __fadd_rn(__fsub_rn(hi, __fsub_rn(s, bb)), __fsub_rn(x, bb));
+    hi = s;
+    lo = __fadd_rn(lo, e);
+}
+
+// FarnebackUpdateFlow_Blur, column-marching (see above).  What bounds this kernel on B200 is the
+// number of shared-memory wavefronts and the quarter-rate XU conversions, not DRAM (ncu, profiles/):
+//   * the vertical 15-row running sums are float-float pairs updated with TwoSum on the FMA pipe (a
+//     plain float running sum would keep eps*|edge value| of error in flat areas next to strong edges;
+//     OpenCV uses double here) -- no FP64, no float<->double conversion per row;
+//   * the shared rows are 32-bit (half the wavefronts of double rows);
+//   * the horizontal 15-tap sums are plain float sums (core + suffix + prefix, no sliding window, so
+//     no error persists) with a dependent chain of 8;
+//   * only the 2x2 solve runs in double (5 + 4 conversions per output).
 __global__ void __launch_bounds__(MS_W)
 k_fb_blur_solve(const float *__restrict__ M, int h, int w, float2 *__restrict__ flow, int rows_per_block)
 {
-    // kept in double: float<->double conversions run on the quarter-rate XU pipe (profiles/r01_notes.md)
-    __shared__ double row[5][MS_ROWP];
-    __shared__ double hs[5][MS_HSP];
+    __shared__ float row[5][MS_ROWP];
+    __shared__ float hs[5][MS_HSP];
     const int pair = blockIdx.z, t = threadIdx.x;
     const size_t plane = (size_t)h * w;
     const float *src = M + (size_t)pair * 5 * plane;
     const int sx0 = blockIdx.x * MS_OUT, y0 = blockIdx.y * rows_per_block;
     const int gx = clampi(sx0 - 8 + t, 0, w - 1);
     const int y_end = min(y0 + rows_per_block, h);
-    double vs[5];
+    float vh[5], vl[5];
 #pragma unroll
-    for (int c = 0; c < 5; c++) vs[c] = 0;
+    for (int c = 0; c < 5; c++) vh[c] = vl[c] = 0.f;
     for (int k = -MS_R; k <= MS_R; k++) {
         const float *p = src + (size_t)clampi(y0 + k, 0, h - 1) * w + gx;
 #pragma unroll
-        for (int c = 0; c < 5; c++) vs[c] += (double)__ldg(p + c * plane);
+        for (int c = 0; c < 5; c++) ff_add(vh[c], vl[c], __ldg(p + c * plane));
     }
     const int hc = t / 14, hseg = t - hc * 14;                      // horizontal work item (t < 70)
     const int ox = t - 8, gxo = sx0 + ox;                           // output column of this thread
     const bool has_out = ox >= 0 && ox < MS_OUT && gxo < w;
     // shared-memory cursors with compile-time offsets (pad: one extra word per 8 columns)
-    double *my_row = &row[0][ms_pad(t)];
-    const double *hin = &row[t < 70 ? hc : 0][ms_pad((t < 70 ? hseg : 0) * MS_SEG + 1)];   // taps of output o: columns o+1 .. o+15
-    double *hout = &hs[t < 70 ? hc : 0][ms_pad((t < 70 ? hseg : 0) * MS_SEG)];
-    const double *my_hs = &hs[0][ms_pad(has_out ? ox : 0)];
+    float *my_row = &row[0][ms_pad(t)];
+    const float *hin = &row[t < 70 ? hc : 0][ms_pad((t < 70 ? hseg : 0) * MS_SEG + 1)];   // taps of output o: columns o+1 .. o+15
+    float *hout = &hs[t < 70 ? hc : 0][ms_pad((t < 70 ? hseg : 0) * MS_SEG)];
+    const float *my_hs = &hs[0][ms_pad(has_out ? ox : 0)];
     float2 *fout = flow + (size_t)pair * plane + (size_t)y0 * w + (has_out ? gxo : 0);
     // rows entering (yi) / leaving (yo) the 15-row window when the output row advances to y+1
     int yi = y0 + 1 + MS_R, yo = y0 - MS_R;
@@ -459,25 +478,29 @@ k_fb_blur_solve(const float *__restrict__ M, int h, int w, float2 *__restrict__ 
             yo++;
         }
 #pragma unroll
-        for (int c = 0; c < 5; c++) my_row[c * MS_ROWP] = vs[c];
+        for (int c = 0; c < 5; c++) my_row[c * MS_ROWP] = __fadd_rn(vh[c], vl[c]);
         __syncthreads();
         if (t < 70) {
             // element k of the 22-column span sits at padded offset k + ((k + 1) >> 3) from `hin`
-            double s = 0;
+            float p[22];
 #pragma unroll
-            for (int k = 0; k < 2 * MS_R + 1; k++) s += hin[k + ((k + 1) >> 3)];
-            hout[0] = s;
+            for (int k = 0; k < 22; k++) p[k] = hin[k + ((k + 1) >> 3)];
+            const float core = ((p[7] + p[8]) + (p[9] + p[10])) + ((p[11] + p[12]) + (p[13] + p[14]));
+            float L[8], R[8];
+            L[7] = 0.f;
 #pragma unroll
-            for (int j = 1; j < MS_SEG; j++) {
-                s += hin[(j + 2 * MS_R) + ((j + 2 * MS_R + 1) >> 3)] - hin[(j - 1) + (j >> 3)];
-                hout[j] = s;
-            }
+            for (int j = 6; j >= 0; j--) L[j] = L[j + 1] + p[j];
+            R[0] = 0.f;
+#pragma unroll
+            for (int j = 1; j < 8; j++) R[j] = R[j - 1] + p[14 + j];
+#pragma unroll
+            for (int j = 0; j < MS_SEG; j++) hout[j] = (core + L[j]) + R[j];
         }
         __syncthreads();
         if (has_out) {
             const double scale = 1.0 / 225.0;
-            const double g11 = my_hs[0] * scale, g12 = my_hs[MS_HSP] * scale, g22 = my_hs[2 * MS_HSP] * scale;
-            const double h1 = my_hs[3 * MS_HSP] * scale, h2 = my_hs[4 * MS_HSP] * scale;
+            const double g11 = (double)my_hs[0] * scale, g12 = (double)my_hs[MS_HSP] * scale, g22 = (double)my_hs[2 * MS_HSP] * scale;
+            const double h1 = (double)my_hs[3 * MS_HSP] * scale, h2 = (double)my_hs[4 * MS_HSP] * scale;
             // 1/det: float reciprocal seed + two Newton steps in double (relative error < 1e-15)
             const double det = g11 * g22 - g12 * g12 + 1e-3;
             double idet = (double)__frcp_rn((float)det);
@@ -491,7 +514,10 @@ k_fb_blur_solve(const float *__restrict__ M, int h, int w, float2 *__restrict__ 
         fout += w;
         if (more) {
 #pragma unroll
-            for (int c = 0; c < 5; c++) vs[c] += (double)nin[c] - (double)nout[c];
+            for (int c = 0; c < 5; c++) {
+                ff_add(vh[c], vl[c], nin[c]);
+                ff_add(vh[c], vl[c], -nout[c]);
+            }
         }
     }
 }
