@@ -184,6 +184,8 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"           # keep stdout to the single JSON line
         dist.init_process_group("nccl", device_id=dev)
     ctx = N.get_context(local)
     ctx.use_torch_stream()

@@ -17,6 +17,21 @@ namespace vqa {
 constexpr int CT_W = 64, CT_H = 16;           // output tile
 constexpr int LBL_FLAG = 0x40000000, LBL_MASK = 0x3fffffff;
 
+// union-find on tile-local labels in shared memory (same atomicMin scheme as the global one)
+__device__ __forceinline__ void sm_union(int *L, int a, int b)
+{
+    volatile int *V = L;                           // other threads update L with atomics
+    while (true) {
+        while (V[a] != a) a = V[a];
+        while (V[b] != b) b = V[b];
+        if (a == b) return;
+        if (a < b) { int t = a; a = b; b = t; }
+        int old = atomicMin(&L[a], b);
+        if (old == a) return;
+        a = old;
+    }
+}
+
 __global__ void __launch_bounds__(256)
 k_canny_nms(const uint8_t *__restrict__ gray, int h, int w, int low, int high, uint8_t *__restrict__ state,
             int *__restrict__ label)
@@ -24,6 +39,7 @@ k_canny_nms(const uint8_t *__restrict__ gray, int h, int w, int low, int high, u
     __shared__ uint8_t px[CT_H + 4][CT_W + 4];
     __shared__ int mag[CT_H + 2][CT_W + 2];
     __shared__ uint8_t st[CT_H][CT_W];
+    __shared__ int lab[CT_H * CT_W];                 // tile-local union-find (indices inside the tile)
     const int frame = blockIdx.z;
     const uint8_t *g = gray + (size_t)frame * h * w;
     const int tx0 = blockIdx.x * CT_W, ty0 = blockIdx.y * CT_H;
@@ -50,7 +66,7 @@ k_canny_nms(const uint8_t *__restrict__ gray, int h, int w, int low, int high, u
     for (int i = threadIdx.x; i < CT_H * CT_W; i += 256) {
         int ty = i / CT_W, tx = i - ty * CT_W;
         int iy = ty0 + ty, ix = tx0 + tx;
-        if (iy >= h || ix >= w) continue;
+        if (iy >= h || ix >= w) { st[ty][tx] = 0; continue; }      // outside the image: never an edge
         int my = ty + 1, mx = tx + 1, m = mag[my][mx];
         uint8_t s = 0;
         if (m > low) {
@@ -74,15 +90,40 @@ k_canny_nms(const uint8_t *__restrict__ gray, int h, int w, int low, int high, u
         state[(size_t)frame * h * w + (size_t)iy * w + ix] = s;
     }
     __syncthreads();
-    // initial label = leftmost pixel of the horizontal run inside this tile: the union-find then only
-    // has to stitch runs vertically / diagonally and across tile borders
+    // Tile-local connected components in shared memory: (1) label = leftmost pixel of the horizontal
+    // run, (2) stitch runs to the row above (N, else NW / NE) with a shared-memory union-find,
+    // (3) flatten and publish the GLOBAL index of the local root.  The global union-find
+    // (k_ccl_merge) then only has to stitch across tile borders.
+    for (int i = threadIdx.x; i < CT_H * CT_W; i += 256) {
+        int ty = i / CT_W, tx = i - ty * CT_W;
+        int l = -1;
+        if (st[ty][tx]) {
+            int x0 = tx;
+            while (x0 > 0 && st[ty][x0 - 1]) x0--;
+            l = ty * CT_W + x0;
+        }
+        lab[i] = l;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < CT_H * CT_W; i += 256) {
+        int ty = i / CT_W, tx = i - ty * CT_W;
+        if (ty == 0 || !st[ty][tx]) continue;
+        const bool west = tx > 0 && st[ty][tx - 1];
+        if (st[ty - 1][tx]) {
+            if (!(west && st[ty - 1][tx - 1])) sm_union(lab, i, i - CT_W);       // the west pixel already links the same two runs
+        } else {
+            if (tx > 0 && st[ty - 1][tx - 1] && !west) sm_union(lab, i, i - CT_W - 1);
+            if (tx < CT_W - 1 && st[ty - 1][tx + 1]) sm_union(lab, i, i - CT_W + 1);
+        }
+    }
+    __syncthreads();
     for (int i = threadIdx.x; i < CT_H * CT_W; i += 256) {
         int ty = i / CT_W, tx = i - ty * CT_W;
         int iy = ty0 + ty, ix = tx0 + tx;
         if (iy >= h || ix >= w || !st[ty][tx]) continue;
-        int x0 = tx;
-        while (x0 > 0 && st[ty][x0 - 1]) x0--;
-        label[(size_t)frame * h * w + (size_t)iy * w + ix] = iy * w + tx0 + x0;
+        int r = i;
+        while (lab[r] != r) r = lab[r];
+        label[(size_t)frame * h * w + (size_t)iy * w + ix] = (ty0 + r / CT_W) * w + tx0 + (r % CT_W);
     }
 }
 
@@ -116,17 +157,20 @@ k_ccl_merge(const uint8_t *__restrict__ state, int h, int w, int *__restrict__ l
     for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
         if (!s[i]) continue;
         const int y = i / w, x = i - y * w;
-        const bool west = x > 0 && s[i - 1];
-        const bool tile_edge = (x % CT_W) == 0;
-        if (west && tile_edge) uf_union(L, i, i - 1);          // runs are pre-linked inside a tile only
-        if (y > 0) {
-            if (s[i - w]) {
-                // N(i-1) and N(i) adjacent in the same tile belong to one run, as do i-1 and i: skip the duplicate
-                if (!(west && !tile_edge && s[i - w - 1])) uf_union(L, i, i - w);
-            } else {
-                if (x > 0 && s[i - w - 1] && !(west && !tile_edge)) uf_union(L, i, i - w - 1);
+        const int tx = x % CT_W, ty = y % CT_H;
+        if (ty != 0 && tx != 0 && tx != CT_W - 1) continue;     // interior pixels were stitched inside their tile
+        if (tx == 0 && x > 0 && s[i - 1]) uf_union(L, i, i - 1);
+        if (y == 0) continue;
+        const bool north = s[i - w] != 0;
+        if (ty == 0) {                                           // row above lies in another tile
+            if (north) uf_union(L, i, i - w);
+            else {
+                if (x > 0 && s[i - w - 1]) uf_union(L, i, i - w - 1);
                 if (x < w - 1 && s[i - w + 1]) uf_union(L, i, i - w + 1);
             }
+        } else if (!north) {                                     // only the diagonal neighbour across the side border
+            if (tx == 0 && x > 0 && s[i - w - 1]) uf_union(L, i, i - w - 1);
+            if (tx == CT_W - 1 && x < w - 1 && s[i - w + 1]) uf_union(L, i, i - w + 1);
         }
     }
 }

@@ -248,13 +248,23 @@ __global__ void k_entropy(const uint32_t *__restrict__ hist, int n, float *__res
     }
 }
 
+// sum of squares of a uint8 plane: 128-bit loads + dp4a (4 u8*u8 products per instruction)
 __global__ void __launch_bounds__(256)
 k_sq_sum(const uint8_t *__restrict__ x, long per_frame, unsigned long long *__restrict__ out)
 {
     const int frame = blockIdx.y;
     const uint8_t *p = x + (size_t)frame * per_frame;
     unsigned long long acc = 0;
-    for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < per_frame; i += (long)gridDim.x * 256) {
+    const long nvec = ((reinterpret_cast<uintptr_t>(p) & 15) == 0) ? per_frame / 16 : 0;
+    for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < nvec; i += (long)gridDim.x * 256) {
+        const uint4 v = ld_stream(reinterpret_cast<const uint4 *>(p) + i);
+        unsigned s = __dp4a(v.x, v.x, 0u);
+        s = __dp4a(v.y, v.y, s);
+        s = __dp4a(v.z, v.z, s);
+        s = __dp4a(v.w, v.w, s);
+        acc += s;
+    }
+    for (long i = nvec * 16 + (long)blockIdx.x * 256 + threadIdx.x; i < per_frame; i += (long)gridDim.x * 256) {
         unsigned v = p[i];
         acc += v * v;
     }
@@ -314,7 +324,7 @@ int run_entropy(vqa_ctx *c, const uint32_t *hist, int n, float *hist_entropy, fl
 int run_sq_sum(vqa_ctx *c, const uint8_t *x, int n, long per_frame, unsigned long long *out)
 {
     VQA_CUDA(c, cudaMemsetAsync(out, 0, sizeof(unsigned long long) * (size_t)n, c->stream));
-    int bpf = cdiv(per_frame, 256 * 16);
+    int bpf = cdiv(per_frame, 256 * 16 * 4);
     if (bpf < 1) bpf = 1;
     VQA_BYTES(c, (double)per_frame * n);
     VQA_LAUNCH(c, k_sq_sum, dim3(bpf, n), 256, 0, x, per_frame, out);

@@ -210,6 +210,42 @@ def test_analyze_clip_equals_the_two_halves(ctx, synth, small_clip, monkeypatch)
             assert np.array_equal(fr[f], b[f]), f
 
 
+@pytest.mark.parametrize("h,w", [(20, 24), (33, 70), (64, 64), (65, 127), (200, 31)])
+def test_small_and_ragged_sizes(ctx, h, w):
+    """Edge geometries: below the 32-px pyramid limit (single Farneback level), odd sizes, sizes that
+    are not multiples of the vector widths / tile sizes, up-scaling resize targets."""
+    rng = np.random.default_rng(h * 1000 + w)
+    base = rng.integers(0, 256, (h + 8, w + 8, 3), dtype=np.uint8)
+    base = (base.astype(np.float32) * 0.5 + np.roll(base, 2, axis=1).astype(np.float32) * 0.5).astype(np.uint8)
+    clip = np.stack([np.ascontiguousarray(base[i:i + h, 2 * i:2 * i + w]) for i in range(3)])
+    for rw, rh in ((w, h), (64, 64), (w + 5, h + 3)):
+        rows = ctx.complexity_frames(clip, rw, rh)
+        for i, f in enumerate(clip):
+            assert int(rows["edge_count"][i]) == int(RP.o_edge(f, rw, rh)), (rw, rh, i)
+            assert int(rows["orb_count"][i]) == RP.o_orb(f)
+            assert float(rows["hist_entropy"][i]) == pytest.approx(float(RP.o_hist(f, rw, rh)), rel=2e-6, abs=1e-6)
+            assert float(rows["color_entropy"][i]) == pytest.approx(float(RP.o_color(f, rw, rh)), rel=2e-6, abs=1e-6)
+            assert float(rows["dct_energy"][i]) == pytest.approx(float(RP.o_dct(f, rw, rh)), rel=RTOL)
+            if i:
+                assert float(rows["motion"][i]) == pytest.approx(float(RP.o_motion((f, clip[i - 1]))), rel=RTOL, abs=1e-6)
+                g0, g1 = NO.dct_input(clip[i - 1], rw, rh), NO.dct_input(f, rw, rh)
+                assert float(rows["temporal_dct"][i]) == pytest.approx(float(RP.o_tdct(g0, g1, rw, rh)), rel=RTOL)
+
+
+def test_empty_and_single_frame_inputs(ctx, small_clip):
+    assert len(ctx.complexity_frames(small_clip[:0], 64, 64)) == 0
+    one = ctx.complexity_frames(small_clip[:1], 64, 64)
+    assert len(one) == 1 and np.isnan(one["motion"][0]) and np.isnan(one["temporal_dct"][0])
+    assert one["edge_count"][0] == ctx.complexity_frames(small_clip, 64, 64)["edge_count"][0]
+    from rtvqa_b200 import _native as N
+    only_edges = ctx.complexity_frames(small_clip[:2], 64, 64, mask=N.M_EDGE)
+    assert only_edges["orb_count"][0] == -1 and np.isnan(only_edges["dct_energy"][0]) and only_edges["edge_count"][0] >= 0
+    with pytest.raises(N.VqaError):
+        ctx.complexity_frames(small_clip, 0, 64)
+    with pytest.raises(TypeError):
+        ctx.complexity_frames(small_clip.astype(np.float32), 64, 64)
+
+
 def test_zero_and_constant_frames(ctx):
     z = np.zeros((2, 48, 64, 3), np.uint8)
     r = ctx.complexity_frames(z, 64, 64)
