@@ -310,7 +310,13 @@ def run_b200(args):
     if os.path.exists(traffic_file):
         try:
             with open(traffic_file) as f:
-                roofline["traffic"] = json.load(f).get(tname)
+                t = json.load(f).get(tname)
+            if t and t.get("ratio"):
+                # DRAM bytes per launch = (dram bytes / algorithmic bytes of the ncu-captured level-0 launch)
+                # x this run's algorithmic bytes per launch (launches differ in size across pyramid levels)
+                roofline["traffic"] = t["ratio"] * roofline["algorithmic_bytes_per_launch"]
+                roofline["traffic_source"] = {"report": t["report"], "captured_dram_bytes": t["dram_bytes"],
+                                              "captured_algorithmic_bytes": t["algorithmic_bytes"], "ratio": t["ratio"]}
         except Exception:
             pass
 
