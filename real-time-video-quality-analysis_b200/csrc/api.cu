@@ -120,7 +120,10 @@ int vqa_init(int device, vqa_ctx **out)
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess) {
         delete c;
         return set_err(nullptr, VQA_E_CUDA, "stream creation failed");
     }
@@ -142,6 +145,7 @@ void vqa_destroy(vqa_ctx *c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     cudaStreamSynchronize(c->copy_stream);
+    cudaStreamSynchronize(c->side_stream);
     dct_umma_release(c);
     for (auto &kv : c->bufs) if (kv.second.p) cudaFree(kv.second.p);
     for (auto &kv : c->pinned) if (kv.second.p) cudaFreeHost(kv.second.p);
@@ -151,6 +155,9 @@ void vqa_destroy(vqa_ctx *c)
     cudaEventDestroy(c->ev_sync);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     cudaStreamDestroy(c->copy_stream);
+    cudaStreamDestroy(c->side_stream);
+    cudaEventDestroy(c->ev_fork);
+    cudaEventDestroy(c->ev_join);
     delete c;
 }
 
@@ -259,6 +266,13 @@ static int pick_chunk(vqa_ctx *c, int h, int w, int rw, int rh, unsigned mask)
 namespace {
 // Extra host->device copies that ride the copy stream BETWEEN the complexity chunks (the planes of the
 // full-reference half in vqa_analyze_clip): one stream, deterministic order, chunk copies always first.
+// Runs the launches of a scope on another stream of the context (every run_* launcher uses c->stream).
+struct StreamSwap {
+    vqa_ctx *c;
+    cudaStream_t saved;
+    StreamSwap(vqa_ctx *c_, cudaStream_t s) : c(c_), saved(c_->stream) { c->stream = s; }
+    ~StreamSwap() { c->stream = saved; }
+};
 struct SideCopy { uint8_t *dst; const uint8_t *src; size_t bytes, done; };
 struct SideLoad {
     std::vector<SideCopy> copies;
@@ -329,6 +343,7 @@ int complexity_impl(vqa_ctx *c, const uint8_t *bgr, int n, int h, int w, size_t 
         in[0] = in0; in[1] = in1; in[2] = in2;
     }
     const int nchunks = cdiv(n, CH);
+    static const bool use_side = !(getenv("VQA_SIDE_STREAM") && atoi(getenv("VQA_SIDE_STREAM")) == 0);
     auto h2d_chunk = [&](int ci) -> int {
         const int s = ci * CH, m = std::min(CH, n - s);
         if (frame_stride == FB) {
@@ -399,32 +414,41 @@ int complexity_impl(vqa_ctx *c, const uint8_t *bgr, int n, int h, int w, size_t 
         }
         if (want_hist) if ((rc = run_entropy(c, d_hist, m, d_hent + s, d_cent + s))) return rc;
         stage_end(c, "ingest");
-        // ---- Canny
-        if (want_edge) {
-            stage_begin(c, "canny");
-            if ((rc = run_canny(c, identity ? Gc : gs, m, rh, rw, d_edge + s, nullptr))) return rc;
-            stage_end(c, "canny");
+        // ---- Canny, ORB, DCT: independent of the Farneback chain -> a second stream, so the ALU /
+        // latency / tensor-bound kernels of this chain fill the gaps of the DRAM- and LSU-bound flow
+        // kernels (joined at the end of the chunk)
+        const bool fork = use_side && !c->ktiming && want_motion && (want_edge || want_orb || want_dct);
+        if (fork) {
+            VQA_CUDA(c, cudaEventRecord(c->ev_fork, c->stream));
+            VQA_CUDA(c, cudaStreamWaitEvent(c->side_stream, c->ev_fork, 0));
         }
-        // ---- ORB (64x64)
-        if (want_orb) {
-            stage_begin(c, "orb");
-            if ((rc = run_orb64(c, src, m, h, w, stride, d_orb + s))) return rc;
-            stage_end(c, "orb");
-        }
-        // ---- DCT energy + temporal L1
-        if (want_dct) {
-            stage_begin(c, "dct");
-            const uint8_t *X = identity ? Gc : xs + RR;
-            if ((rc = run_dct(c, X, m, rh, rw, cfg->dct_impl, Cbuf + RR, d_energy + s))) return rc;
-            if ((rc = run_sq_sum(c, X, m, (long)RR, d_sq + s))) return rc;
-            if (want_tdct) {
-                const int first = has_prev ? 0 : 1;
-                if (m - first > 0)
-                    if ((rc = run_abs_diff_sum(c, Cbuf + (size_t)first * RR, Cbuf + (size_t)(first + 1) * RR, m - first,
-                                               (long)RR, RR, RR, d_tdct + s + first))) return rc;
-                VQA_CUDA(c, cudaMemcpyAsync(Cbuf, Cbuf + (size_t)m * RR, sizeof(float) * RR, cudaMemcpyDeviceToDevice, c->stream));
+        {
+            StreamSwap sw(c, fork ? c->side_stream : c->stream);
+            if (want_edge) {
+                stage_begin(c, "canny");
+                if ((rc = run_canny(c, identity ? Gc : gs, m, rh, rw, d_edge + s, nullptr))) return rc;
+                stage_end(c, "canny");
             }
-            stage_end(c, "dct");
+            if (want_orb) {
+                stage_begin(c, "orb");
+                if ((rc = run_orb64(c, src, m, h, w, stride, d_orb + s))) return rc;
+                stage_end(c, "orb");
+            }
+            if (want_dct) {
+                stage_begin(c, "dct");
+                const uint8_t *X = identity ? Gc : xs + RR;
+                if ((rc = run_dct(c, X, m, rh, rw, cfg->dct_impl, Cbuf + RR, d_energy + s))) return rc;
+                if ((rc = run_sq_sum(c, X, m, (long)RR, d_sq + s))) return rc;
+                if (want_tdct) {
+                    const int first = has_prev ? 0 : 1;
+                    if (m - first > 0)
+                        if ((rc = run_abs_diff_sum(c, Cbuf + (size_t)first * RR, Cbuf + (size_t)(first + 1) * RR, m - first,
+                                                   (long)RR, RR, RR, d_tdct + s + first))) return rc;
+                    VQA_CUDA(c, cudaMemcpyAsync(Cbuf, Cbuf + (size_t)m * RR, sizeof(float) * RR, cudaMemcpyDeviceToDevice, c->stream));
+                }
+                stage_end(c, "dct");
+            }
+            if (fork) VQA_CUDA(c, cudaEventRecord(c->ev_join, c->stream));
         }
         // ---- Farneback motion
         if (want_motion) {
@@ -434,6 +458,7 @@ int complexity_impl(vqa_ctx *c, const uint8_t *bgr, int n, int h, int w, size_t 
                 if ((rc = run_farneback(c, G + (size_t)first * HW, m - first, h, w, d_mag + s + first, nullptr))) return rc;
             stage_end(c, "motion");
         }
+        if (fork) VQA_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));     // join before gray / staging are reused
         if (want_motion || want_tdct)
             VQA_CUDA(c, cudaMemcpyAsync(G, G + (size_t)m * HW, HW, cudaMemcpyDeviceToDevice, c->stream));
         if (!on_device) VQA_CUDA(c, cudaEventRecord(c->ev_done[ci % 3], c->stream));

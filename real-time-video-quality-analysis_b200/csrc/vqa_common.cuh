@@ -38,6 +38,8 @@ struct vqa_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;
+    cudaStream_t side_stream = nullptr;          // Canny / ORB / DCT chain of a chunk, concurrent with the Farneback chain
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool own_stream = false;
     int sm_count = 148;
     char err[512] = {0};
