@@ -270,7 +270,7 @@ def run_b200(args):
     sampler.start()
     sec_dev, launches, out = timed(step_device, args.steps, args.warmup)
     clocks = sampler.summary()
-    sec_e2e, _, out_e2e = timed(step_e2e, max(1, min(args.steps, 5)), 1)
+    sec_e2e, _, out_e2e = timed(step_e2e, max(1, min(args.steps, 5)), 2)
     e2e_steps = max(1, min(args.steps, 5))
 
     analysed = F - 1 if world == 1 else F               # pairs per rank: rank 0 has no halo
