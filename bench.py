@@ -76,39 +76,61 @@ def make_yuv_pairs_device(clip_dev, seed):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """SM clock / power / throttle reasons DURING the timed region (B200_PROFILING.md), every 100 ms.
+    NVML in-process (nvidia_ml_py); falls back to spawning nvidia-smi.  (Spawning nvidia-smi every
+    200 ms perturbed the step time by ~10 %: each invocation holds driver locks for ~150 ms.)"""
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self.stop_flag = index, [], threading.Event()
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        except Exception:
+            self.nvml = None
 
-    def run(self):
+    def _sample_nvml(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+        pw = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+        r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
+            else n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
+        self.rows.append((float(sm), float(mx), pw, {k for k, b in bits.items() if r & b}))
+
+    def _sample_smi(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout
+        f = [x.strip() for x in out.strip().split(",")]
+        if len(f) >= 7:
+            names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+            self.rows.append((float(f[0]), float(f[1]), float(f[2]),
+                              {n_ for n_, v in zip(names, f[3:7]) if v.lower().startswith("active")}))
+
+    def run(self):
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                f = [s.strip() for s in out.strip().split(",")]
-                if len(f) >= 7:
-                    self.rows.append(f)
+                self._sample_nvml() if self.nvml else self._sample_smi()
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.1 if self.nvml else 1.0)
 
     def summary(self):
         self.stop_flag.set()
         self.join(timeout=6)
         if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
-        reasons = []
-        for name, col in (("hw_slowdown", 3), ("hw_thermal_slowdown", 4), ("sw_thermal_slowdown", 5), ("sw_power_cap", 6)):
-            if any(r[col].lower().startswith("active") for r in self.rows):
-                reasons.append(name)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]),
-                "power_w_max": max(float(r[2]) for r in self.rows), "samples": len(self.rows), "reasons": reasons}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"]}
+        sm = sorted(r[0] for r in self.rows)
+        reasons = sorted(set().union(*[r[3] for r in self.rows]))
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.rows[0][1], "power_w_max": max(r[2] for r in self.rows),
+                "samples": len(self.rows), "source": "nvml" if self.nvml else "nvidia-smi", "reasons": reasons}
 
 
 # ----------------------------------------------------------------------------- CPU arm

@@ -38,7 +38,7 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
     for s in SOURCES:
         src, obj = os.path.join(CSRC, s), os.path.join(OBJ, s[:-3] + ".o")
         if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hdr_m):
-            cmd = [nvcc, *NVCC_FLAGS, "-c", src, "-o", obj]
+            cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("VQA_NVCC_EXTRA", "").split(), "-c", src, "-o", obj]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
             jobs.append(cmd)
