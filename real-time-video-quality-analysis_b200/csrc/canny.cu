@@ -3,8 +3,7 @@
 //   k_canny_nms     Sobel 3x3 (replicate border) + L1 magnitude (zero ring) + non-maximum
 //                   suppression with OpenCV's TG22 fixed-point sectors -> 0 / 1 (weak) / 2 (strong)
 //   k_ccl_merge     8-connected union-find over kept pixels (atomicMin on roots)
-//   k_ccl_flatten   every kept pixel points at its root
-//   k_ccl_mark      roots of components that contain a strong pixel get a flag bit
+//   k_ccl_flatten   every kept pixel points at its root; roots of components with a strong pixel get a flag bit
 //   k_ccl_count     count (and optionally paint) the kept pixels of flagged components
 //
 // Hysteresis is a connected-components problem: the fix-point is unique, so the count equals
@@ -175,30 +174,21 @@ k_ccl_merge(const uint8_t *__restrict__ state, int h, int w, int *__restrict__ l
     }
 }
 
+// every kept pixel points at its root; roots of components that contain a strong pixel get the flag
+// (a root's own entry is never rewritten by the flatten, so the flag survives; readers mask it)
 __global__ void __launch_bounds__(256)
 k_ccl_flatten(const uint8_t *__restrict__ state, int total, int *__restrict__ label)
 {
     const int frame = blockIdx.y;
     const uint8_t *s = state + (size_t)frame * total;
     int *L = label + (size_t)frame * total;
-    for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256)
-        if (s[i]) {
-            int r = uf_find(L, i);
-            if (r != i) L[i] = r;
-        }
-}
-
-__global__ void __launch_bounds__(256)
-k_ccl_mark(const uint8_t *__restrict__ state, int total, int *__restrict__ label)
-{
-    const int frame = blockIdx.y;
-    const uint8_t *s = state + (size_t)frame * total;
-    int *L = label + (size_t)frame * total;
-    for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256)
-        if (s[i] == 2) {
-            int r = L[i] & LBL_MASK;
-            if (!(L[r] & LBL_FLAG)) atomicOr(&L[r], LBL_FLAG);
-        }
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
+        const uint8_t st = s[i];
+        if (!st) continue;
+        const int r = uf_find(L, i);
+        if (r != i) L[i] = r;
+        if (st == 2 && !(__ldcg(L + r) & LBL_FLAG)) atomicOr(&L[r], LBL_FLAG);
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -236,8 +226,6 @@ int run_canny(vqa_ctx *c, const uint8_t *gray, int n, int h, int w, unsigned lon
     VQA_LAUNCH(c, k_ccl_merge, g2, 256, 0, state, h, w, label);
     VQA_BYTES(c, 1.0 * total * n);
     VQA_LAUNCH(c, k_ccl_flatten, g2, 256, 0, state, (int)total, label);
-    VQA_BYTES(c, 1.0 * total * n);
-    VQA_LAUNCH(c, k_ccl_mark, g2, 256, 0, state, (int)total, label);
     VQA_BYTES(c, 1.0 * total * n);
     VQA_LAUNCH(c, k_ccl_count, g2, 256, 0, state, (int)total, label, counts, edges_out);
     return VQA_OK;

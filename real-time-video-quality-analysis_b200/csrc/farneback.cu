@@ -112,8 +112,10 @@ k_fb_pyramid(const uint8_t *__restrict__ gray, int H, int W, int lh, int lw, int
         const int xo = xtab[p];
         for (int ry = tid / hbw; ry < RH; ry += rstep) {
             const uint8_t *c = src + ry * rw_pitch + xo;
+            // (float)(a + b) == (float)a + (float)b exactly for 8-bit a, b: one int->float conversion
+            // (quarter-rate XU pipe) per symmetric tap pair instead of two
             float s = taps.k[r] * (float)c[0];
-            for (int k = 1; k <= r; k++) s += taps.k[r + k] * ((float)c[-k] + (float)c[k]);
+            for (int k = 1; k <= r; k++) s += taps.k[r + k] * (float)((int)c[-k] + (int)c[k]);
             hb[ry * hbw + p] = s;
         }
     }
@@ -490,7 +492,8 @@ __device__ __forceinline__ void ff_add(float &hi, float &lo, float x)
 //     no error persists) with a dependent chain of 8;
 //   * only the 2x2 solve runs in double (5 + 4 conversions per output).
 __global__ void __launch_bounds__(MS_W)
-k_fb_blur_solve(const float *__restrict__ M, int h, int w, float2 *__restrict__ flow, int rows_per_block)
+k_fb_blur_solve(const float *__restrict__ M, int h, int w, float2 *__restrict__ flow, int rows_per_block,
+                double *__restrict__ mag_sum, int write_flow)
 {
     __shared__ float row[5][MS_ROWP];
     __shared__ float hs[5][MS_HSP];
@@ -521,6 +524,7 @@ k_fb_blur_solve(const float *__restrict__ M, int h, int w, float2 *__restrict__ 
     int yi = y0 + 1 + MS_R, yo = y0 - MS_R;
     const float *pin = src + (size_t)clampi(yi, 0, h - 1) * w + gx, *pout = src + (size_t)clampi(yo, 0, h - 1) * w + gx;
     float nin[5], nout[5];
+    double mag_acc = 0;
     for (int y = y0; y < y_end; y++) {
         const bool more = y + 1 < y_end;
         if (more) {
@@ -563,7 +567,10 @@ k_fb_blur_solve(const float *__restrict__ M, int h, int w, float2 *__restrict__ 
             float2 o;
             o.x = (float)((g11 * h2 - g12 * h1) * idet);
             o.y = (float)((g22 * h1 - g12 * h2) * idet);
-            *fout = o;
+            if (write_flow) *fout = o;
+            // last iteration of level 0: the flow field itself is not needed any more, only
+            // sum |flow| (cartToPolar magnitude, complexity_metrics.py:342-343)
+            if (mag_sum) mag_acc += (double)sqrtf(__fadd_rn(__fmul_rn(o.x, o.x), __fmul_rn(o.y, o.y)));
         }
         fout += w;
         if (more) {
@@ -572,6 +579,18 @@ k_fb_blur_solve(const float *__restrict__ M, int h, int w, float2 *__restrict__ 
                 ff_add(vh[c], vl[c], nin[c]);
                 ff_add(vh[c], vl[c], -nout[c]);
             }
+        }
+    }
+    if (mag_sum) {
+        __shared__ double red[MS_W / 32];
+        mag_acc = warp_sum(mag_acc);
+        __syncthreads();
+        if ((t & 31) == 0) red[t >> 5] = mag_acc;
+        __syncthreads();
+        if (t == 0) {
+            double sum = 0;
+            for (int i = 0; i < MS_W / 32; i++) sum += red[i];
+            atomicAdd(&mag_sum[pair], sum);
         }
     }
 }
@@ -670,6 +689,7 @@ int run_farneback(vqa_ctx *c, const uint8_t *gray, int npairs, int h, int w, dou
     static const int pe_f32 = getenv("VQA_PE_F32") ? atoi(getenv("VQA_PE_F32")) : 1;
     PolyConst pc;
     make_poly(pc);
+    VQA_CUDA(c, cudaMemsetAsync(mag_sum, 0, sizeof(double) * (size_t)npairs, c->stream));
     float2 *flow = flowA, *prev = flowB;
     int ph = 0, pw = 0;
     for (int k = levels; k >= 0; k--) {
@@ -727,7 +747,9 @@ int run_farneback(vqa_ctx *c, const uint8_t *gray, int npairs, int h, int w, dou
         }
         for (int it = 0; it < 3; it++) {
             VQA_BYTES(c, 28.0 * lw * lh * npairs);
-            VQA_LAUNCH(c, k_fb_blur_solve, dim3(cdiv(lw, MS_OUT), cdiv(lh, rows_pb), npairs), MS_W, 0, M, lh, lw, flow, rows_pb);
+            const bool last = (k == 0 && it == 2);
+            VQA_LAUNCH(c, k_fb_blur_solve, dim3(cdiv(lw, MS_OUT), cdiv(lh, rows_pb), npairs), MS_W, 0, M, lh, lw, flow, rows_pb,
+                       last ? mag_sum : (double *)nullptr, (!last || flow_out) ? 1 : 0);
             if (it < 2) {
                 VQA_BYTES(c, 68.0 * lw * lh * npairs);
                 if ((lw & 3) == 0 && mat_v4) {
@@ -740,12 +762,8 @@ int run_farneback(vqa_ctx *c, const uint8_t *gray, int npairs, int h, int w, dou
         float2 *t = prev; prev = flow; flow = t;
         ph = lh; pw = lw;
     }
-    // `prev` now holds the level-0 flow
-    VQA_CUDA(c, cudaMemsetAsync(mag_sum, 0, sizeof(double) * (size_t)npairs, c->stream));
-    int bpf = cdiv((long)full, 256 * 8);
-    if (bpf < 1) bpf = 1;
-    VQA_BYTES(c, 8.0 * full * npairs);
-    VQA_LAUNCH(c, k_fb_mag_sum, dim3(bpf, npairs), 256, 0, prev, (long)full, mag_sum);
+    // `prev` now holds the level-0 flow (only written when the caller asked for it); sum |flow| was
+    // accumulated by the last blur pass
     if (flow_out)
         VQA_CUDA(c, cudaMemcpyAsync(flow_out, prev, sizeof(float2) * full * npairs, cudaMemcpyDeviceToDevice, c->stream));
     return VQA_OK;

@@ -246,6 +246,40 @@ def test_empty_and_single_frame_inputs(ctx, small_clip):
         ctx.complexity_frames(small_clip.astype(np.float32), 64, 64)
 
 
+def test_padded_frame_stride_through_the_raw_abi(ctx, small_clip):
+    """frame_stride > h*w*3 (frames embedded in a larger buffer), host and device pointers."""
+    import ctypes as C
+    import torch
+    from rtvqa_b200 import _native as N
+    n, h, w, _ = small_clip.shape
+    fb, stride = h * w * 3, h * w * 3 + 208
+    buf = np.zeros(n * stride, np.uint8)
+    for i in range(n):
+        buf[i * stride:i * stride + fb] = small_clip[i].reshape(-1)
+    want = ctx.complexity_frames(small_clip, 64, 64)
+    cfg = N.Cfg(64, 64, N.M_ALL, 0)
+    for on_dev in (0, 1):
+        out = np.zeros(n, dtype=N.FRAME_DTYPE)
+        if on_dev:
+            t = torch.from_numpy(buf).cuda()
+            torch.cuda.synchronize()
+            ptr = t.data_ptr()
+        else:
+            ptr = buf.ctypes.data
+        rc = ctx.lib.vqa_complexity_frames(ctx.h, C.c_void_p(ptr), n, h, w, stride, None, on_dev, C.byref(cfg),
+                                           C.c_void_p(out.ctypes.data))
+        assert rc == 0, ctx.lib.vqa_last_error(ctx.h)
+        for f in want.dtype.names:
+            assert np.array_equal(out[f], want[f], equal_nan=True), (on_dev, f)
+    # error codes, not exceptions, across the ABI
+    out = np.zeros(n, dtype=N.FRAME_DTYPE)
+    assert ctx.lib.vqa_complexity_frames(ctx.h, C.c_void_p(buf.ctypes.data), n, h, w, fb - 1, None, 0, C.byref(cfg),
+                                         C.c_void_p(out.ctypes.data)) == -1
+    assert b"frame_stride" in ctx.lib.vqa_last_error(ctx.h)
+    assert ctx.lib.vqa_complexity_frames(None, C.c_void_p(buf.ctypes.data), n, h, w, fb, None, 0, C.byref(cfg),
+                                         C.c_void_p(out.ctypes.data)) == -1
+
+
 def test_zero_and_constant_frames(ctx):
     z = np.zeros((2, 48, 64, 3), np.uint8)
     r = ctx.complexity_frames(z, 64, 64)

@@ -9,7 +9,7 @@ def alg_bytes(kernel, grid):
     g = [int(v) for v in re.findall(r"\d+", grid)]
     z = g[2] if len(g) > 2 else 1
     if "k_fb_blur_solve" in kernel: return 28.0 * HW * z
-    if "k_fb_matrices<0>" in kernel: return 68.0 * HW * z
+    if "k_fb_matrices<0>" in kernel or "k_fb_matrices_v4<0>" in kernel: return 68.0 * HW * z
     if "k_fb_matrices<1>" in kernel: return (60.0 * HW + 8.0 * HW / 4) * z
     if "k_fb_polyexp" in kernel: return 24.0 * HW * z
     if "k_canny_nms" in kernel: return 2.0 * HW * z
@@ -19,7 +19,7 @@ def alg_bytes(kernel, grid):
 
 def norm(name):
     n = name.split("(")[0].replace("void ", "").replace(" ", "")
-    n = n.replace("<128,", "<BN,").replace("vqa::", "")
+    n = n.replace("<256,1>", "<BN1,1>").replace("<128,2>", "<BN2,2>").replace("vqa::", "")
     n = re.sub(r"k_gray_hist<1,0>", "k_gray_hist<true,false>", n)
     return n
 
