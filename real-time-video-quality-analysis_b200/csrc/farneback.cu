@@ -8,7 +8,7 @@
 //     k_fb_upsample     flow = 2 * resize_f32(flow_{k+1})  (zeros at the coarsest level)
 //     k_fb_matrices     M    = UpdateMatrices(R_prev, R_cur, flow)                   per PAIR
 //     3 x k_fb_blur_solve  flow = solve2x2(boxmean15x15(M));  M rebuilt after iterations 1, 2
-//   k_fb_mag_sum        sum sqrt(fx^2 + fy^2) at level 0
+//   (last blur pass)    sum sqrt(fx^2 + fy^2) at level 0, fused into k_fb_blur_solve
 //
 // R is computed once per frame and serves the frame both as "next" of one pair and as "prev"
 // of the following pair.  R, M and flow stay fp32 (reduced precision does not survive flat
@@ -71,6 +71,8 @@ constexpr int PY_TW = 32, PY_TH = 8;
 // loading) -> horizontal Gaussian at the <= 64 source columns the tile samples -> vertical Gaussian
 // at the <= 2 rows each output samples -> area / bilinear combine.  Evaluation order matches
 // OpenCV's separable float32 filter (rows then columns, centre tap + symmetric pairs).
+// RT > 0: Gaussian radius known at compile time (taps in registers, loops unrolled); RT = 0: generic
+template <int RT>
 __global__ void __launch_bounds__(PY_TW * PY_TH)
 k_fb_pyramid(const uint8_t *__restrict__ gray, int H, int W, int lh, int lw, int mode, GaussTaps taps,
              float *__restrict__ I, int rw_pitch)
@@ -80,7 +82,12 @@ k_fb_pyramid(const uint8_t *__restrict__ gray, int H, int W, int lh, int lw, int
     const int frame = blockIdx.z, tid = threadIdx.x;
     const uint8_t *img = gray + (size_t)frame * H * W;
     const int tx0 = blockIdx.x * PY_TW, ty0 = blockIdx.y * PY_TH;
-    const int r = taps.ksz >> 1, np = mode == 0 ? 1 : 2;
+    const int r = RT > 0 ? RT : (taps.ksz >> 1), np = mode == 0 ? 1 : 2;
+    float tk[RT > 0 ? RT + 1 : 1];                                     // tk[k] = tap at distance k from the centre
+    if (RT > 0) {
+#pragma unroll
+        for (int k = 0; k <= RT; k++) tk[k] = taps.k[RT + k];
+    }
     int p0, p1, q0, q1;
     float fa;
     py_tap(tx0, W, lw, mode, false, p0, q0, fa);
@@ -114,8 +121,15 @@ k_fb_pyramid(const uint8_t *__restrict__ gray, int H, int W, int lh, int lw, int
             const uint8_t *c = src + ry * rw_pitch + xo;
             // (float)(a + b) == (float)a + (float)b exactly for 8-bit a, b: one int->float conversion
             // (quarter-rate XU pipe) per symmetric tap pair instead of two
-            float s = taps.k[r] * (float)c[0];
-            for (int k = 1; k <= r; k++) s += taps.k[r + k] * (float)((int)c[-k] + (int)c[k]);
+            float s;
+            if (RT > 0) {
+                s = tk[0] * (float)c[0];
+#pragma unroll
+                for (int k = 1; k <= RT; k++) s += tk[k] * (float)((int)c[-k] + (int)c[k]);
+            } else {
+                s = taps.k[r] * (float)c[0];
+                for (int k = 1; k <= r; k++) s += taps.k[r + k] * (float)((int)c[-k] + (int)c[k]);
+            }
             hb[ry * hbw + p] = s;
         }
     }
@@ -131,8 +145,15 @@ k_fb_pyramid(const uint8_t *__restrict__ gray, int H, int W, int lh, int lw, int
         const int yy = (wy ? yb : ya) - y_lo;
         for (int wx = 0; wx < np; wx++) {
             const float *c = hb + (size_t)yy * hbw + (tid & (PY_TW - 1)) * np + wx;
-            float s = taps.k[r] * c[0];
-            for (int k = 1; k <= r; k++) s += taps.k[r + k] * (c[-k * hbw] + c[k * hbw]);
+            float s;
+            if (RT > 0) {
+                s = tk[0] * c[0];
+#pragma unroll
+                for (int k = 1; k <= RT; k++) s += tk[k] * (c[-k * hbw] + c[k * hbw]);
+            } else {
+                s = taps.k[r] * c[0];
+                for (int k = 1; k <= r; k++) s += taps.k[r + k] * (c[-k * hbw] + c[k * hbw]);
+            }
             v[wy][wx] = s;
         }
     }
@@ -595,27 +616,6 @@ k_fb_blur_solve(const float *__restrict__ M, int h, int w, float2 *__restrict__ 
     }
 }
 
-__global__ void __launch_bounds__(256)
-k_fb_mag_sum(const float2 *__restrict__ flow, long plane, double *__restrict__ out)
-{
-    __shared__ double red[8];
-    const int pair = blockIdx.y;
-    const float2 *f = flow + (size_t)pair * plane;
-    double acc = 0;
-    for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < plane; i += (long)gridDim.x * 256) {
-        const float2 v = f[i];
-        acc += (double)sqrtf(__fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y)));
-    }
-    acc = warp_sum(acc);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double s = 0;
-        for (int i = 0; i < 8; i++) s += red[i];
-        atomicAdd(&out[pair], s);
-    }
-}
-
 // ---------------------------------------------------------------------------------- host side
 static void make_gauss(int ksz, double sigma, GaussTaps &t)
 {
@@ -710,15 +710,20 @@ int run_farneback(vqa_ctx *c, const uint8_t *gray, int npairs, int h, int w, dou
             const int rhm = (int)ceil(PY_TH * sy) + 2 * (ksz / 2) + 4;
             const size_t smem = (((size_t)rhm * rwp + 15) & ~(size_t)15) + (size_t)rhm * 2 * PY_TW * sizeof(float);
             if (smem > 200 * 1024) return set_err(c, VQA_E_UNSUPPORTED, "farneback pyramid tile needs %zu B of shared memory", smem);
-            if (smem > 48 * 1024)
-                VQA_CUDA(c, cudaFuncSetAttribute(k_fb_pyramid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (smem > 48 * 1024) {
+                VQA_CUDA(c, cudaFuncSetAttribute(k_fb_pyramid<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                VQA_CUDA(c, cudaFuncSetAttribute(k_fb_pyramid<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                VQA_CUDA(c, cudaFuncSetAttribute(k_fb_pyramid<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            }
             VQA_BYTES(c, ((double)full + 4.0 * lw * lh) * nf);
             if (ksz == 3 && mode == 0) {
                 VQA_LAUNCH(c, k_fb_pyramid3<0>, dim3(cdiv(w, 128), cdiv(h, 8), nf), 256, 0, gray, h, w, lh, lw, taps.k[0], taps.k[1], I);
             } else if (ksz == 3 && mode == 1) {
                 VQA_LAUNCH(c, k_fb_pyramid3<1>, dim3(cdiv(w, 128), cdiv(h, 16), nf), 256, 0, gray, h, w, lh, lw, taps.k[0], taps.k[1], I);
             } else {
-                VQA_LAUNCH(c, k_fb_pyramid, gF, PY_TW * PY_TH, smem, gray, h, w, lh, lw, mode, taps, I, rwp);
+                if (ksz == 19) VQA_LAUNCH(c, k_fb_pyramid<9>, gF, PY_TW * PY_TH, smem, gray, h, w, lh, lw, mode, taps, I, rwp);
+                else if (ksz == 9) VQA_LAUNCH(c, k_fb_pyramid<4>, gF, PY_TW * PY_TH, smem, gray, h, w, lh, lw, mode, taps, I, rwp);
+                else VQA_LAUNCH(c, k_fb_pyramid<0>, gF, PY_TW * PY_TH, smem, gray, h, w, lh, lw, mode, taps, I, rwp);
             }
         }
         VQA_BYTES(c, 24.0 * lw * lh * nf);
