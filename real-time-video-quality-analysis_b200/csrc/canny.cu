@@ -35,58 +35,104 @@ __global__ void __launch_bounds__(256)
 k_canny_nms(const uint8_t *__restrict__ gray, int h, int w, int low, int high, uint8_t *__restrict__ state,
             int *__restrict__ label)
 {
-    __shared__ uint8_t px[CT_H + 4][CT_W + 4];
-    __shared__ int mag[CT_H + 2][CT_W + 2];
-    __shared__ uint8_t st[CT_H][CT_W];
-    __shared__ int lab[CT_H * CT_W];                 // tile-local union-find (indices inside the tile)
+    // Packed front end: the pixel tile is held as 32-bit words (image columns tx0-4 .. tx0+67), a work
+    // item produces 4 adjacent gradient magnitudes from 6 word loads, and the NMS of 4 adjacent pixels
+    // reads the stored (dx, dy) instead of re-deriving them (the byte-wise version was ALU-bound, SM 86 %).
+    constexpr int PXW = (CT_W + 8) / 4, MGP = CT_W + 4;            // 18 words per pixel row; mag / sobel pitch 68
+    __shared__ uint32_t px[CT_H + 4][PXW];
+    __shared__ __align__(16) int mag[CT_H + 2][MGP];
+    __shared__ __align__(16) int sob[CT_H + 2][MGP];               // (dy << 16) | (dx & 0xffff)
+    __shared__ __align__(4) uint8_t st[CT_H][CT_W];
+    __shared__ int lab[CT_H * CT_W];                               // tile-local union-find (indices inside the tile)
     const int frame = blockIdx.z;
     const uint8_t *g = gray + (size_t)frame * h * w;
     const int tx0 = blockIdx.x * CT_W, ty0 = blockIdx.y * CT_H;
-    for (int i = threadIdx.x; i < (CT_H + 4) * (CT_W + 4); i += 256) {
-        int y = i / (CT_W + 4), x = i - y * (CT_W + 4);
-        int gy = clampi(ty0 - 2 + y, 0, h - 1), gx = clampi(tx0 - 2 + x, 0, w - 1);
-        px[y][x] = g[(size_t)gy * w + gx];
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < (CT_H + 2) * (CT_W + 2); i += 256) {
-        int my = i / (CT_W + 2), mx = i - my * (CT_W + 2);
-        int iy = ty0 - 1 + my, ix = tx0 - 1 + mx, m = 0;
-        if (iy >= 0 && iy < h && ix >= 0 && ix < w) {
-            int cy = my + 1, cx = mx + 1;
-            int dx = (px[cy - 1][cx + 1] + 2 * px[cy][cx + 1] + px[cy + 1][cx + 1]) -
-                     (px[cy - 1][cx - 1] + 2 * px[cy][cx - 1] + px[cy + 1][cx - 1]);
-            int dy = (px[cy + 1][cx - 1] + 2 * px[cy + 1][cx] + px[cy + 1][cx + 1]) -
-                     (px[cy - 1][cx - 1] + 2 * px[cy - 1][cx] + px[cy - 1][cx + 1]);
-            m = abs(dx) + abs(dy);
+    const bool w4 = (w & 3) == 0;
+    const bool xin = w4 && tx0 >= 4 && tx0 + CT_W + 4 <= w;        // all 18 words inside the row
+    for (int i = threadIdx.x; i < (CT_H + 4) * PXW; i += 256) {
+        const int y = i / PXW, wd = i - y * PXW;
+        const uint8_t *row = g + (size_t)clampi(ty0 - 2 + y, 0, h - 1) * w;
+        const int gx = tx0 - 4 + wd * 4;
+        uint32_t v;
+        if (xin) v = __ldg(reinterpret_cast<const uint32_t *>(row + gx));
+        else {
+            v = 0;
+#pragma unroll
+            for (int b = 0; b < 4; b++) v |= (uint32_t)__ldg(row + clampi(gx + b, 0, w - 1)) << (8 * b);
         }
-        mag[my][mx] = m;
+        px[y][wd] = v;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < CT_H * CT_W; i += 256) {
-        int ty = i / CT_W, tx = i - ty * CT_W;
-        int iy = ty0 + ty, ix = tx0 + tx;
-        if (iy >= h || ix >= w) { st[ty][tx] = 0; continue; }      // outside the image: never an edge
-        int my = ty + 1, mx = tx + 1, m = mag[my][mx];
-        uint8_t s = 0;
-        if (m > low) {
-            int cy = ty + 2, cx = tx + 2;
-            int xs = (px[cy - 1][cx + 1] + 2 * px[cy][cx + 1] + px[cy + 1][cx + 1]) -
-                     (px[cy - 1][cx - 1] + 2 * px[cy][cx - 1] + px[cy + 1][cx - 1]);
-            int ys = (px[cy + 1][cx - 1] + 2 * px[cy + 1][cx] + px[cy + 1][cx + 1]) -
-                     (px[cy - 1][cx - 1] + 2 * px[cy - 1][cx] + px[cy - 1][cx + 1]);
-            int ax = abs(xs), ay = abs(ys) << 15;
-            int t = ax * 13573;
-            bool keep;
-            if (ay < t) keep = m > mag[my][mx - 1] && m >= mag[my][mx + 1];
-            else if (ay > t + (ax << 16)) keep = m > mag[my - 1][mx] && m >= mag[my + 1][mx];
-            else {
-                int sgn = (xs ^ ys) < 0 ? -1 : 1;
-                keep = m > mag[my - 1][mx - sgn] && m > mag[my + 1][mx + sgn];
+    // gradient magnitudes (and dx, dy) of mag columns 4q .. 4q+3 of mag row my; mag (my, mx) is image
+    // pixel (ty0 - 1 + my, tx0 - 1 + mx), whose tile byte column is mx + 3
+    for (int i = threadIdx.x; i < (CT_H + 2) * (MGP / 4); i += 256) {
+        const int my = i / (MGP / 4), q = i - my * (MGP / 4);
+        int r[3][6];                                               // byte columns 4q+2 .. 4q+7 of tile rows my .. my+2
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const uint32_t w0 = px[my + k][q], w1 = px[my + k][q + 1];
+            r[k][0] = (w0 >> 16) & 255; r[k][1] = w0 >> 24;
+            r[k][2] = w1 & 255; r[k][3] = (w1 >> 8) & 255; r[k][4] = (w1 >> 16) & 255; r[k][5] = w1 >> 24;
+        }
+        int cs[6];
+#pragma unroll
+        for (int j = 0; j < 6; j++) cs[j] = r[0][j] + 2 * r[1][j] + r[2][j];
+        const int iy = ty0 - 1 + my;
+        int m4[4], s4[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int ix = tx0 - 1 + 4 * q + k;
+            const int dx = cs[k + 2] - cs[k];
+            const int dy = (r[2][k] + 2 * r[2][k + 1] + r[2][k + 2]) - (r[0][k] + 2 * r[0][k + 1] + r[0][k + 2]);
+            const bool in = iy >= 0 && iy < h && ix >= 0 && ix < w;
+            m4[k] = in ? abs(dx) + abs(dy) : 0;
+            s4[k] = (int)(((unsigned)dy << 16) | ((unsigned)dx & 0xffffu));
+        }
+        *reinterpret_cast<int4 *>(&mag[my][4 * q]) = make_int4(m4[0], m4[1], m4[2], m4[3]);
+        *reinterpret_cast<int4 *>(&sob[my][4 * q]) = make_int4(s4[0], s4[1], s4[2], s4[3]);
+    }
+    __syncthreads();
+    {
+        const int ty = threadIdx.x >> 4, q = threadIdx.x & 15;      // pixels tx = 4q .. 4q+3 of tile row ty
+        const int iy = ty0 + ty, my = ty + 1;
+        int mrow[3][6];                                            // mag columns 4q .. 4q+5 of rows my-1 .. my+1
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const int4 a = *reinterpret_cast<const int4 *>(&mag[my - 1 + k][4 * q]);
+            const int2 b = *reinterpret_cast<const int2 *>(&mag[my - 1 + k][4 * q + 4]);
+            mrow[k][0] = a.x; mrow[k][1] = a.y; mrow[k][2] = a.z; mrow[k][3] = a.w; mrow[k][4] = b.x; mrow[k][5] = b.y;
+        }
+        uint32_t packed = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int ix = tx0 + 4 * q + k, c = k + 1;             // c: column of this pixel inside mrow
+            const int m = mrow[1][c];
+            uint32_t sv = 0;
+            if (iy < h && ix < w && m > low) {
+                const int sd = sob[my][4 * q + c];
+                const int xs = (int)(short)(sd & 0xffff), ys = sd >> 16;
+                const int ax = abs(xs), ay = abs(ys) << 15;
+                const int t = ax * 13573;
+                bool keep;
+                if (ay < t) keep = m > mrow[1][c - 1] && m >= mrow[1][c + 1];
+                else if (ay > t + (ax << 16)) keep = m > mrow[0][c] && m >= mrow[2][c];
+                else {
+                    const bool neg = (xs ^ ys) < 0;              // sgn = -1: compare with (N, x+1) and (S, x-1)
+                    keep = m > (neg ? mrow[0][c + 1] : mrow[0][c - 1]) && m > (neg ? mrow[2][c - 1] : mrow[2][c + 1]);
+                }
+                if (keep) sv = m > high ? 2u : 1u;
             }
-            if (keep) s = m > high ? 2 : 1;
+            packed |= sv << (8 * k);
         }
-        st[ty][tx] = s;
-        state[(size_t)frame * h * w + (size_t)iy * w + ix] = s;
+        *reinterpret_cast<uint32_t *>(&st[ty][4 * q]) = packed;
+        if (iy < h) {
+            const int ix0 = tx0 + 4 * q;
+            uint8_t *dst = state + (size_t)frame * h * w + (size_t)iy * w + ix0;
+            if (w4 && ix0 + 4 <= w) *reinterpret_cast<uint32_t *>(dst) = packed;
+            else
+                for (int k = 0; k < 4; k++)
+                    if (ix0 + k < w) dst[k] = (uint8_t)(packed >> (8 * k));
+        }
     }
     __syncthreads();
     // Tile-local connected components in shared memory: (1) label = leftmost pixel of the horizontal
