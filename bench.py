@@ -76,7 +76,7 @@ def make_yuv_pairs_device(clip_dev, seed):
 
 
 class ClockSampler(threading.Thread):
-    """SM clock / power / throttle reasons DURING the timed region (B200_PROFILING.md), every 100 ms.
+    """SM clock / power / throttle reasons DURING the timed region (B200_PROFILING.md), every 50 ms.
     NVML in-process (nvidia_ml_py); falls back to spawning nvidia-smi.  (Spawning nvidia-smi every
     200 ms perturbed the step time by ~10 %: each invocation holds driver locks for ~150 ms.)"""
 
@@ -120,7 +120,7 @@ class ClockSampler(threading.Thread):
                 self._sample_nvml() if self.nvml else self._sample_smi()
             except Exception:
                 pass
-            self.stop_flag.wait(0.1 if self.nvml else 1.0)
+            self.stop_flag.wait(0.05 if self.nvml else 1.0)
 
     def summary(self):
         self.stop_flag.set()
@@ -129,7 +129,15 @@ class ClockSampler(threading.Thread):
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"]}
         sm = sorted(r[0] for r in self.rows)
         reasons = sorted(set().union(*[r[3] for r in self.rows]))
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.rows[0][1], "power_w_max": max(r[2] for r in self.rows),
+        out_extra = {}
+        if self.nvml:
+            try:
+                out_extra["power_limit_w"] = self.nvml.nvmlDeviceGetEnforcedPowerLimit(self.handle) / 1000.0
+            except Exception:
+                pass
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.rows[0][1], "sm_mhz_min": sm[0],
+                "sm_mhz_mean": round(sum(sm) / len(sm), 1), "power_w_max": max(r[2] for r in self.rows),
+                "power_w_mean": round(sum(r[2] for r in self.rows) / len(self.rows), 1), **out_extra,
                 "samples": len(self.rows), "source": "nvml" if self.nvml else "nvidia-smi", "reasons": reasons}
 
 

@@ -1,5 +1,6 @@
 // extern "C" entry points of libvqa_b200.so (include/vqa_b200.h): context, scratch arena, the
 // chunked/double-buffered clip pipeline and the stage-level debug taps.
+#include <chrono>
 #include <math.h>
 #include <stdarg.h>
 #include <stdlib.h>
@@ -33,6 +34,7 @@ void *dev_buf(vqa_ctx *c, const char *name, size_t bytes)
         b.cap = 0;
     }
     size_t cap = (bytes + 255) & ~(size_t)255;
+    c->alloc_epoch++;
     cudaError_t e = cudaMalloc(&b.p, cap);
     if (e != cudaSuccess) {
         b.p = nullptr;
@@ -41,6 +43,17 @@ void *dev_buf(vqa_ctx *c, const char *name, size_t bytes)
     }
     b.cap = cap;
     return b.p;
+}
+
+size_t free_device_memory(vqa_ctx *c)
+{
+    if (c->free_epoch != c->alloc_epoch) {
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        c->free_cached = free_b;
+        c->free_epoch = c->alloc_epoch;
+    }
+    return c->free_cached;
 }
 
 void *pinned_buf(vqa_ctx *c, const char *name, size_t bytes)
@@ -128,13 +141,14 @@ int vqa_init(int device, vqa_ctx **out)
         return set_err(nullptr, VQA_E_CUDA, "stream creation failed");
     }
     c->own_stream = true;
+    const unsigned wait_flag = (getenv("VQA_SPIN_WAIT") && atoi(getenv("VQA_SPIN_WAIT"))) ? 0u : (unsigned)cudaEventBlockingSync;
     for (int i = 0; i < 3; i++) {
         cudaEventCreateWithFlags(&c->ev_copy[i], cudaEventDisableTiming);
         // host waits on these must yield, not spin: a spinning waiter in a second thread (the FR half)
         // slowed the kernel-launching thread of the complexity half enough to serialise the two
-        cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming | cudaEventBlockingSync);
+        cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming | wait_flag);
     }
-    cudaEventCreateWithFlags(&c->ev_sync, cudaEventDisableTiming | cudaEventBlockingSync);
+    cudaEventCreateWithFlags(&c->ev_sync, cudaEventDisableTiming | wait_flag);
     *out = c;
     return VQA_OK;
 }
@@ -247,8 +261,7 @@ static int pick_chunk(vqa_ctx *c, int h, int w, int rw, int rh, unsigned mask)
 {
     const char *env = getenv("VQA_CHUNK");
     if (env && atoi(env) > 0) return atoi(env);
-    size_t free_b = 0, total_b = 0;
-    cudaMemGetInfo(&free_b, &total_b);
+    const size_t free_b = free_device_memory(c);
     const double hw = (double)h * w, rr = (double)rw * rh;
     double per = hw * 3 * 3 + hw * 2 + rr * 8;                         // input double buffer, gray, labels/state
     if (mask & VQA_M_MOTION) per += hw * 66;                           // I, R, M, 2 x flow
@@ -296,6 +309,8 @@ int complexity_impl(vqa_ctx *c, const uint8_t *bgr, int n, int h, int w, size_t 
                     int on_device, const vqa_cfg *cfg, vqa_frame_metrics *out, SideLoad *side)
 {
     if (!c) return VQA_E_INVALID;
+    static const bool host_trace = getenv("VQA_HOST_TRACE") && atoi(getenv("VQA_HOST_TRACE"));
+    const auto t_host0 = std::chrono::steady_clock::now();
     if (!bgr || !cfg || !out || n < 0 || h <= 0 || w <= 0)
         return set_err(c, VQA_E_INVALID, "vqa_complexity_frames: bad argument");
     if (n == 0) return VQA_OK;
@@ -497,7 +512,14 @@ int complexity_impl(vqa_ctx *c, const uint8_t *bgr, int n, int h, int w, size_t 
     if (want_motion) D2H(hr.mag, d_mag, double);
     if (want_orb) D2H(hr.orb, d_orb, int);
 #undef D2H
+    const auto t_host1 = std::chrono::steady_clock::now();
     VQA_CUDA(c, wait_stream(c));
+    if (host_trace) {
+        const auto t_host2 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[vqa] complexity n=%d: host enqueue %.2f ms, drained after %.2f ms\n", n,
+                std::chrono::duration<double, std::milli>(t_host1 - t_host0).count(),
+                std::chrono::duration<double, std::milli>(t_host2 - t_host0).count());
+    }
     const float nanf_ = nanf("");
     for (int i = 0; i < n; i++) {
         vqa_frame_metrics &o = out[i];
@@ -543,8 +565,7 @@ int vqa_analyze_clip(vqa_ctx *c, const uint8_t *bgr, int n, int h, int w, size_t
         pb[p] = (size_t)plane_h[p] * stride[p] * n_pairs;
         tot += 2 * pb[p];
     }
-    size_t free_b = 0, total_b = 0;
-    cudaMemGetInfo(&free_b, &total_b);
+    const size_t free_b = free_device_memory(c);
     if (tot > free_b / 4) {                            // does not fit beside the complexity scratch: run the halves in turn
         int rc = vqa_psnr_ssim_planar(c, main_planes, ref_planes, plane_w, plane_h, stride, n_pairs, 0, fr_out);
         if (rc) return rc;

@@ -403,9 +403,11 @@ __device__ __forceinline__ void fb_matrix_core(float q0, float q1, float q2, flo
     r2 += r4 * dy + r6 * dx;
     r3 += r6 * dy + r5 * dx;
     if ((unsigned)(x - 5) >= (unsigned)(w - 10) || (unsigned)(y - 5) >= (unsigned)(h - 10)) {
-        const float border[5] = {0.14f, 0.14f, 0.4472f, 0.4472f, 0.4472f};
-        const float sc = (x < 5 ? border[x] : 1.f) * (x >= w - 5 ? border[w - x - 1] : 1.f) *
-                         (y < 5 ? border[y] : 1.f) * (y >= h - 5 ? border[h - y - 1] : 1.f);
+        // OpenCV's border[] = {0.14, 0.14, 0.4472, 0.4472, 0.4472} by distance to the edge
+#define FB_BORDER(d) ((d) < 2 ? 0.14f : 0.4472f)
+        const float sc = (x < 5 ? FB_BORDER(x) : 1.f) * (x >= w - 5 ? FB_BORDER(w - x - 1) : 1.f) *
+                         (y < 5 ? FB_BORDER(y) : 1.f) * (y >= h - 5 ? FB_BORDER(h - y - 1) : 1.f);
+#undef FB_BORDER
         r2 *= sc; r3 *= sc; r4 *= sc; r5 *= sc; r6 *= sc;
     }
     m[0] = r4 * r4 + r6 * r6;
@@ -487,10 +489,15 @@ constexpr int MS_W = 128, MS_OUT = 112, MS_R = 7, MS_H = 96, MS_SEG = 8;
 // running sum would keep eps*|edge value| of error in flat areas next to strong edges), so each row
 // costs one incoming + one outgoing load per plane.  The horizontal 15-tap sums are built from the
 // shared row of vertical sums by 70 work items (5 planes x 14 segments of 8 outputs), sliding in double.
-// shared rows are padded by one word every 8 so that the 14 segment work items of a plane (stride 8)
-// fall into distinct banks
-__device__ __forceinline__ int ms_pad(int i) { return i + (i >> 3); }
-constexpr int MS_ROWP = MS_W + MS_W / 8 + 1, MS_HSP = MS_OUT + MS_OUT / 8 + 1;
+// Shared-memory layout of the row of vertical sums and of the horizontal sums: logical column i of a
+// plane lives at word i + 4*(i >> 5) (four pad words after every 32).  With it all four access
+// patterns are bank-conflict free: (A) thread t stores column t (an aligned group of 32 per warp),
+// (B) work item (plane, segment s) loads columns 8s .. 8s+23 as six 128-bit words (a quarter-warp of
+// eight segments covers all 32 banks exactly once), (C) it stores its eight sums as two 128-bit
+// words, (D) thread t loads the sums of output column t - 8, stored at index t.  The earlier
+// "one pad word per 8" layout had 2-way conflicts on (A), (B) and (D) (ncu: 45 % excessive wavefronts).
+__device__ __forceinline__ int ms_sw(int i) { return i + ((i >> 5) << 2); }
+constexpr int MS_VP = 144;
 
 // running sum kept as an unevaluated float pair (hi + lo): Knuth's TwoSum adds x exactly into hi and
 // the rounding error into lo, ~48 significant bits with FP32 adds only
@@ -512,12 +519,18 @@ __device__ __forceinline__ void ff_add(float &hi, float &lo, float x)
 //   * the horizontal 15-tap sums are plain float sums (core + suffix + prefix, no sliding window, so
 //     no error persists) with a dependent chain of 8;
 //   * only the 2x2 solve runs in double (5 + 4 conversions per output).
+//
+// EPI 0: the new flow is stored (last iteration of a level; on level 0 the caller may ask for
+//        sum |flow| instead).  EPI 1: the flow never leaves the registers -- the UpdateMatrices of the
+//        NEXT iteration is pointwise in the pixel, so it is evaluated right here from R0/R1 and the
+//        fresh flow and written to the other M buffer (saves the flow round trip and one launch).
+template <int EPI>
 __global__ void __launch_bounds__(MS_W)
 k_fb_blur_solve(const float *__restrict__ M, int h, int w, float2 *__restrict__ flow, int rows_per_block,
-                double *__restrict__ mag_sum, int write_flow)
+                double *__restrict__ mag_sum, int write_flow, const float *__restrict__ R, float *__restrict__ Mnext)
 {
-    __shared__ float row[5][MS_ROWP];
-    __shared__ float hs[5][MS_HSP];
+    __shared__ __align__(16) float row[5][MS_VP];
+    __shared__ __align__(16) float hs[5][MS_VP];
     const int pair = blockIdx.z, t = threadIdx.x;
     const size_t plane = (size_t)h * w;
     const float *src = M + (size_t)pair * 5 * plane;
@@ -532,14 +545,20 @@ k_fb_blur_solve(const float *__restrict__ M, int h, int w, float2 *__restrict__ 
 #pragma unroll
         for (int c = 0; c < 5; c++) ff_add(vh[c], vl[c], __ldg(p + c * plane));
     }
-    const int hc = t / 14, hseg = t - hc * 14;                      // horizontal work item (t < 70)
+    // horizontal work item: 16 lanes per plane (14 segments of 8 outputs + 2 idle lanes), so that a
+    // quarter-warp of a 128-bit access never mixes planes
+    const int hc = t >> 4, hseg = t & 15;
+    const bool hwork = t < 80 && hseg < 14;
     const int ox = t - 8, gxo = sx0 + ox;                           // output column of this thread
     const bool has_out = ox >= 0 && ox < MS_OUT && gxo < w;
-    // shared-memory cursors with compile-time offsets (pad: one extra word per 8 columns)
-    float *my_row = &row[0][ms_pad(t)];
-    const float *hin = &row[t < 70 ? hc : 0][ms_pad((t < 70 ? hseg : 0) * MS_SEG + 1)];   // taps of output o: columns o+1 .. o+15
-    float *hout = &hs[t < 70 ? hc : 0][ms_pad((t < 70 ? hseg : 0) * MS_SEG)];
-    const float *my_hs = &hs[0][ms_pad(has_out ? ox : 0)];
+    float *my_row = &row[0][ms_sw(t)];
+    const float *hrow = row[hwork ? hc : 0];
+    int hoff[6];
+#pragma unroll
+    for (int j = 0; j < 6; j++) hoff[j] = ms_sw((hwork ? hseg : 0) * MS_SEG + 4 * j);
+    float *hout0 = &hs[hwork ? hc : 0][ms_sw((hwork ? hseg : 0) * MS_SEG + 8)];
+    float *hout1 = &hs[hwork ? hc : 0][ms_sw((hwork ? hseg : 0) * MS_SEG + 12)];
+    const float *my_hs = &hs[0][ms_sw(t)];
     float2 *fout = flow + (size_t)pair * plane + (size_t)y0 * w + (has_out ? gxo : 0);
     // rows entering (yi) / leaving (yo) the 15-row window when the output row advances to y+1
     int yi = y0 + 1 + MS_R, yo = y0 - MS_R;
@@ -557,29 +576,35 @@ k_fb_blur_solve(const float *__restrict__ M, int h, int w, float2 *__restrict__ 
             yo++;
         }
 #pragma unroll
-        for (int c = 0; c < 5; c++) my_row[c * MS_ROWP] = __fadd_rn(vh[c], vl[c]);
+        for (int c = 0; c < 5; c++) my_row[c * MS_VP] = __fadd_rn(vh[c], vl[c]);
         __syncthreads();
-        if (t < 70) {
-            // element k of the 22-column span sits at padded offset k + ((k + 1) >> 3) from `hin`
-            float p[22];
+        if (hwork) {
+            // p[k] = column 8s + k; output o of the segment sums columns 8s+o+1 .. 8s+o+15
+            float p[24];
 #pragma unroll
-            for (int k = 0; k < 22; k++) p[k] = hin[k + ((k + 1) >> 3)];
-            const float core = ((p[7] + p[8]) + (p[9] + p[10])) + ((p[11] + p[12]) + (p[13] + p[14]));
+            for (int j = 0; j < 6; j++) {
+                const float4 v = *reinterpret_cast<const float4 *>(hrow + hoff[j]);
+                p[4 * j] = v.x; p[4 * j + 1] = v.y; p[4 * j + 2] = v.z; p[4 * j + 3] = v.w;
+            }
+            const float core = ((p[8] + p[9]) + (p[10] + p[11])) + ((p[12] + p[13]) + (p[14] + p[15]));
             float L[8], R[8];
             L[7] = 0.f;
 #pragma unroll
-            for (int j = 6; j >= 0; j--) L[j] = L[j + 1] + p[j];
+            for (int j = 6; j >= 0; j--) L[j] = L[j + 1] + p[j + 1];
             R[0] = 0.f;
 #pragma unroll
-            for (int j = 1; j < 8; j++) R[j] = R[j - 1] + p[14 + j];
+            for (int j = 1; j < 8; j++) R[j] = R[j - 1] + p[15 + j];
+            float o8[MS_SEG];
 #pragma unroll
-            for (int j = 0; j < MS_SEG; j++) hout[j] = (core + L[j]) + R[j];
+            for (int j = 0; j < MS_SEG; j++) o8[j] = (core + L[j]) + R[j];
+            *reinterpret_cast<float4 *>(hout0) = make_float4(o8[0], o8[1], o8[2], o8[3]);
+            *reinterpret_cast<float4 *>(hout1) = make_float4(o8[4], o8[5], o8[6], o8[7]);
         }
         __syncthreads();
         if (has_out) {
             const double scale = 1.0 / 225.0;
-            const double g11 = (double)my_hs[0] * scale, g12 = (double)my_hs[MS_HSP] * scale, g22 = (double)my_hs[2 * MS_HSP] * scale;
-            const double h1 = (double)my_hs[3 * MS_HSP] * scale, h2 = (double)my_hs[4 * MS_HSP] * scale;
+            const double g11 = (double)my_hs[0] * scale, g12 = (double)my_hs[MS_VP] * scale, g22 = (double)my_hs[2 * MS_VP] * scale;
+            const double h1 = (double)my_hs[3 * MS_VP] * scale, h2 = (double)my_hs[4 * MS_VP] * scale;
             // 1/det: float reciprocal seed + two Newton steps in double (relative error < 1e-15)
             const double det = g11 * g22 - g12 * g12 + 1e-3;
             double idet = (double)__frcp_rn((float)det);
@@ -588,10 +613,19 @@ k_fb_blur_solve(const float *__restrict__ M, int h, int w, float2 *__restrict__ 
             float2 o;
             o.x = (float)((g11 * h2 - g12 * h1) * idet);
             o.y = (float)((g22 * h1 - g12 * h2) * idet);
-            if (write_flow) *fout = o;
-            // last iteration of level 0: the flow field itself is not needed any more, only
-            // sum |flow| (cartToPolar magnitude, complexity_metrics.py:342-343)
-            if (mag_sum) mag_acc += (double)sqrtf(__fadd_rn(__fmul_rn(o.x, o.x), __fmul_rn(o.y, o.y)));
+            if (EPI == 0) {
+                if (write_flow) *fout = o;
+                // last iteration of level 0: the flow field itself is not needed any more, only
+                // sum |flow| (cartToPolar magnitude, complexity_metrics.py:342-343)
+                if (mag_sum) mag_acc += (double)sqrtf(__fadd_rn(__fmul_rn(o.x, o.x), __fmul_rn(o.y, o.y)));
+            } else {
+                const float *R0 = R + (size_t)pair * 5 * plane;
+                float m[5];
+                fb_matrix_at(R0, R0 + 5 * plane, plane, gxo, y, h, w, o, m);
+                float *dst = Mnext + (size_t)pair * 5 * plane + (size_t)y * w + gxo;
+#pragma unroll
+                for (int c = 0; c < 5; c++) dst[c * plane] = m[c];
+            }
         }
         fout += w;
         if (more) {
@@ -602,7 +636,7 @@ k_fb_blur_solve(const float *__restrict__ M, int h, int w, float2 *__restrict__ 
             }
         }
     }
-    if (mag_sum) {
+    if (EPI == 0 && mag_sum) {
         __shared__ double red[MS_W / 32];
         mag_acc = warp_sum(mag_acc);
         __syncthreads();
@@ -683,6 +717,8 @@ int run_farneback(vqa_ctx *c, const uint8_t *gray, int npairs, int h, int w, dou
     VQA_BUF(c, I, float, "fb.I", full * nf);
     VQA_BUF(c, R, float, "fb.R", full * 5 * nf);
     VQA_BUF(c, M, float, "fb.M", full * 5 * npairs);
+    VQA_BUF(c, M2, float, "fb.M2", full * 5 * npairs);
+    static const int fuse_epi = getenv("VQA_FB_EPI") ? atoi(getenv("VQA_FB_EPI")) : 0;
     VQA_BUF(c, flowA, float2, "fb.flowA", full * npairs);
     VQA_BUF(c, flowB, float2, "fb.flowB", full * npairs);
     static const int mat_v4 = getenv("VQA_MAT_V4") ? atoi(getenv("VQA_MAT_V4")) : 1;
@@ -750,17 +786,26 @@ int run_farneback(vqa_ctx *c, const uint8_t *gray, int npairs, int h, int w, dou
             if (rows_pb < 16) rows_pb = 16;
             if (rows_pb > MS_H) rows_pb = MS_H;
         }
+        float *Mcur = M, *Mnxt = M2;
+        const dim3 gB(cdiv(lw, MS_OUT), cdiv(lh, rows_pb), npairs);
         for (int it = 0; it < 3; it++) {
-            VQA_BYTES(c, 28.0 * lw * lh * npairs);
             const bool last = (k == 0 && it == 2);
-            VQA_LAUNCH(c, k_fb_blur_solve, dim3(cdiv(lw, MS_OUT), cdiv(lh, rows_pb), npairs), MS_W, 0, M, lh, lw, flow, rows_pb,
-                       last ? mag_sum : (double *)nullptr, (!last || flow_out) ? 1 : 0);
+            if (it < 2 && fuse_epi) {
+                // blur + solve + next UpdateMatrices: M 20 + R0 20 + R1 20 read, M' 20 written
+                VQA_BYTES(c, 80.0 * lw * lh * npairs);
+                VQA_LAUNCH(c, k_fb_blur_solve<1>, gB, MS_W, 0, Mcur, lh, lw, flow, rows_pb, (double *)nullptr, 0, R, Mnxt);
+                float *tm = Mcur; Mcur = Mnxt; Mnxt = tm;
+                continue;
+            }
+            VQA_BYTES(c, 28.0 * lw * lh * npairs);
+            VQA_LAUNCH(c, k_fb_blur_solve<0>, gB, MS_W, 0, Mcur, lh, lw, flow, rows_pb,
+                       last ? mag_sum : (double *)nullptr, (!last || flow_out) ? 1 : 0, (const float *)nullptr, (float *)nullptr);
             if (it < 2) {
                 VQA_BYTES(c, 68.0 * lw * lh * npairs);
                 if ((lw & 3) == 0 && mat_v4) {
-                    VQA_LAUNCH(c, k_fb_matrices_v4<0>, dim3(cdiv(lw, 128), cdiv(lh, 8), npairs), 256, 0, R, flow, lh, lw, M, prev, ph, pw);
+                    VQA_LAUNCH(c, k_fb_matrices_v4<0>, dim3(cdiv(lw, 128), cdiv(lh, 8), npairs), 256, 0, R, flow, lh, lw, Mcur, prev, ph, pw);
                 } else {
-                    VQA_LAUNCH(c, k_fb_matrices<0>, gP, 256, 0, R, flow, lh, lw, M, prev, ph, pw);
+                    VQA_LAUNCH(c, k_fb_matrices<0>, gP, 256, 0, R, flow, lh, lw, Mcur, prev, ph, pw);
                 }
             }
         }

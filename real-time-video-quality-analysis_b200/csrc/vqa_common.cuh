@@ -54,12 +54,17 @@ struct vqa_ctx {
     bool ktiming = false;                         // per-kernel CUDA-event timing (bench roofline leg)
     std::map<std::string, vqa::KRec> krec;
     double cur_bytes = 0, cur_flops = 0;          // algorithmic traffic of the NEXT launch
+    // cudaMemGetInfo goes through the kernel driver's resource-manager lock (which monitoring agents
+    // polling NVML hold for tens of ms at a time): asked once per allocation epoch, not once per call
+    uint64_t alloc_epoch = 1, free_epoch = 0;
+    size_t free_cached = 0;
     void *umma = nullptr;                         // tensor-map cache of the tcgen05 DCT (dct_umma.cu)
 };
 
 namespace vqa {
 
 int set_err(vqa_ctx *c, int code, const char *fmt, ...);
+size_t free_device_memory(vqa_ctx *c);
 void *dev_buf(vqa_ctx *c, const char *name, size_t bytes);     // nullptr on failure (error set)
 void *pinned_buf(vqa_ctx *c, const char *name, size_t bytes);
 void stage_begin(vqa_ctx *c, const char *stage);
