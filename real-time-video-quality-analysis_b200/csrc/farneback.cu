@@ -602,17 +602,21 @@ k_fb_blur_solve(const float *__restrict__ M, int h, int w, float2 *__restrict__ 
         }
         __syncthreads();
         if (has_out) {
-            const double scale = 1.0 / 225.0;
-            const double g11 = (double)my_hs[0] * scale, g12 = (double)my_hs[MS_VP] * scale, g22 = (double)my_hs[2 * MS_VP] * scale;
-            const double h1 = (double)my_hs[3 * MS_VP] * scale, h2 = (double)my_hs[4 * MS_VP] * scale;
-            // 1/det: float reciprocal seed + two Newton steps in double (relative error < 1e-15)
-            const double det = g11 * g22 - g12 * g12 + 1e-3;
-            double idet = (double)__frcp_rn((float)det);
-            idet = idet * (2.0 - det * idet);
-            idet = idet * (2.0 - det * idet);
+            // 2x2 solve on the raw window sums s.. (g.. = s.. / 225): OpenCV evaluates
+            // det = g11*g22 - g12^2 + 1e-3 and the two numerators in double; here every a*b - c*d is
+            // formed in float with the product error recovered by FMA (w = c*d, e = fma(-c, d, w),
+            // a*b - c*d = fma(a, b, -w) + e: below 2 ulp even under cancellation), so the XU pipe sees
+            // one reciprocal instead of ten float<->double conversions per output
+            const float s11 = my_hs[0], s12 = my_hs[MS_VP], s22 = my_hs[2 * MS_VP], t1 = my_hs[3 * MS_VP], t2 = my_hs[4 * MS_VP];
+            const float k2 = 1.f / (225.f * 225.f);
+            const float w0 = __fmul_rn(s12, s12), w1 = __fmul_rn(s12, t1), w2 = __fmul_rn(s12, t2);
+            const float det = __fmaf_rn(__fadd_rn(__fmaf_rn(s11, s22, -w0), __fmaf_rn(-s12, s12, w0)), k2, 1e-3f);
+            const float nx = __fadd_rn(__fmaf_rn(s11, t2, -w1), __fmaf_rn(-s12, t1, w1));
+            const float ny = __fadd_rn(__fmaf_rn(s22, t1, -w2), __fmaf_rn(-s12, t2, w2));
+            float idet = __frcp_rn(det);
             float2 o;
-            o.x = (float)((g11 * h2 - g12 * h1) * idet);
-            o.y = (float)((g22 * h1 - g12 * h2) * idet);
+            o.x = __fmul_rn(__fmul_rn(nx, k2), idet);
+            o.y = __fmul_rn(__fmul_rn(ny, k2), idet);
             if (EPI == 0) {
                 if (write_flow) *fout = o;
                 // last iteration of level 0: the flow field itself is not needed any more, only
