@@ -417,6 +417,20 @@ __device__ __forceinline__ void fb_matrix_core(float q0, float q1, float q2, flo
     m[4] = r6 * r2 + r5 * r3;
 }
 
+// Layout of the M field (5 floats per pixel): the linear pixel index p = y*w + x is cut into
+// super-chunks of FB_MS pixels and each super-chunk stores its five planes back to back:
+// [pair][p / FB_MS][plane][p % FB_MS].  Access patterns are those of plain planar storage (each plane a
+// contiguous stream; a layout with the planes of 32 pixels adjacent measured 20 % slower in the
+// UpdateMatrices writer), but the five planes of a pixel sit at the COMPILE-TIME offsets c * 256 KB
+// from one address, so the marching blur kernel issues its ten loads per row from two pointers
+// (runtime plane strides cost a 64-bit add per load and made that kernel issue-bound).
+constexpr int FB_MS_LOG = 16, FB_MS = 1 << FB_MS_LOG;
+__host__ __device__ __forceinline__ size_t fb_m_pair_floats(int h, int w)
+{
+    return (((size_t)h * w + FB_MS - 1) >> FB_MS_LOG) * 5 * FB_MS;
+}
+__device__ __forceinline__ unsigned fb_m_index(unsigned p) { return p + ((p >> FB_MS_LOG) << (FB_MS_LOG + 2)); }
+
 // INIT 0: flow read from memory; 1: flow up-sampled from the previous (coarser) level; 2: zero flow
 template <int INIT>
 __global__ void __launch_bounds__(256)
@@ -434,9 +448,9 @@ k_fb_matrices(const float *__restrict__ R, const float2 *__restrict__ flow, int 
     else f = make_float2(0.f, 0.f);
     float m[5];
     fb_matrix_at(R0, R1, plane, x, y, h, w, f, m);
-    float *dst = M + (size_t)pair * 5 * plane + (size_t)y * w + x;
+    float *dst = M + (size_t)pair * fb_m_pair_floats(h, w) + fb_m_index((unsigned)(y * w + x));
 #pragma unroll
-    for (int c = 0; c < 5; c++) dst[c * plane] = m[c];
+    for (int c = 0; c < 5; c++) dst[c * FB_MS] = m[c];
 }
 
 // UpdateMatrices with the flow read from memory, 4 adjacent pixels per thread: R0, flow and M move
@@ -474,10 +488,10 @@ k_fb_matrices_v4(const float *__restrict__ R, const float2 *__restrict__ flow, i
     for (int j = 0; j < 4; j++)
         fb_matrix_core(QJ(0, j), QJ(1, j), QJ(2, j), QJ(3, j), QJ(4, j), R1, plane, x + j, y, h, w, f[j], m[j]);
 #undef QJ
-    float *dst = M + (size_t)pair * 5 * plane + o;
+    float *dst = M + (size_t)pair * fb_m_pair_floats(h, w) + fb_m_index((unsigned)(y * w + x));
 #pragma unroll
     for (int c = 0; c < 5; c++)
-        *reinterpret_cast<float4 *>(dst + c * plane) = make_float4(m[0][c], m[1][c], m[2][c], m[3][c]);
+        *reinterpret_cast<float4 *>(dst + c * FB_MS) = make_float4(m[0][c], m[1][c], m[2][c], m[3][c]);
 }
 
 constexpr int MS_W = 128, MS_OUT = 112, MS_R = 7, MS_H = 96, MS_SEG = 8;
@@ -533,7 +547,7 @@ k_fb_blur_solve(const float *__restrict__ M, int h, int w, float2 *__restrict__ 
     __shared__ __align__(16) float hs[5][MS_VP];
     const int pair = blockIdx.z, t = threadIdx.x;
     const size_t plane = (size_t)h * w;
-    const float *src = M + (size_t)pair * 5 * plane;
+    const float *src = M + (size_t)pair * fb_m_pair_floats(h, w);
     const int sx0 = blockIdx.x * MS_OUT, y0 = blockIdx.y * rows_per_block;
     const int gx = clampi(sx0 - 8 + t, 0, w - 1);
     const int y_end = min(y0 + rows_per_block, h);
@@ -541,9 +555,9 @@ k_fb_blur_solve(const float *__restrict__ M, int h, int w, float2 *__restrict__ 
 #pragma unroll
     for (int c = 0; c < 5; c++) vh[c] = vl[c] = 0.f;
     for (int k = -MS_R; k <= MS_R; k++) {
-        const float *p = src + (size_t)clampi(y0 + k, 0, h - 1) * w + gx;
+        const float *p = src + fb_m_index((unsigned)(clampi(y0 + k, 0, h - 1) * w + gx));
 #pragma unroll
-        for (int c = 0; c < 5; c++) ff_add(vh[c], vl[c], __ldg(p + c * plane));
+        for (int c = 0; c < 5; c++) ff_add(vh[c], vl[c], __ldg(p + c * FB_MS));
     }
     // horizontal work item: 16 lanes per plane (14 segments of 8 outputs + 2 idle lanes), so that a
     // quarter-warp of a 128-bit access never mixes planes
@@ -562,16 +576,17 @@ k_fb_blur_solve(const float *__restrict__ M, int h, int w, float2 *__restrict__ 
     float2 *fout = flow + (size_t)pair * plane + (size_t)y0 * w + (has_out ? gxo : 0);
     // rows entering (yi) / leaving (yo) the 15-row window when the output row advances to y+1
     int yi = y0 + 1 + MS_R, yo = y0 - MS_R;
-    const float *pin = src + (size_t)clampi(yi, 0, h - 1) * w + gx, *pout = src + (size_t)clampi(yo, 0, h - 1) * w + gx;
+    unsigned p_in = (unsigned)(clampi(yi, 0, h - 1) * w + gx), p_out = (unsigned)(clampi(yo, 0, h - 1) * w + gx);   // linear pixel indices
     float nin[5], nout[5];
     double mag_acc = 0;
     for (int y = y0; y < y_end; y++) {
         const bool more = y + 1 < y_end;
         if (more) {
+            const float *pin = src + fb_m_index(p_in), *pout = src + fb_m_index(p_out);
 #pragma unroll
-            for (int c = 0; c < 5; c++) { nin[c] = __ldg(pin + c * plane); nout[c] = __ldg(pout + c * plane); }
-            pin += (yi >= 0 && yi < h - 1) ? w : 0;                  // replicate border: the pointer stops at rows 0 / h-1
-            pout += (yo >= 0 && yo < h - 1) ? w : 0;
+            for (int c = 0; c < 5; c++) { nin[c] = __ldg(pin + c * FB_MS); nout[c] = __ldg(pout + c * FB_MS); }
+            p_in += ((unsigned)yi < (unsigned)(h - 1)) ? (unsigned)w : 0u;     // replicate border: the row stops at 0 / h-1
+            p_out += ((unsigned)yo < (unsigned)(h - 1)) ? (unsigned)w : 0u;
             yi++;
             yo++;
         }
@@ -626,9 +641,9 @@ k_fb_blur_solve(const float *__restrict__ M, int h, int w, float2 *__restrict__ 
                 const float *R0 = R + (size_t)pair * 5 * plane;
                 float m[5];
                 fb_matrix_at(R0, R0 + 5 * plane, plane, gxo, y, h, w, o, m);
-                float *dst = Mnext + (size_t)pair * 5 * plane + (size_t)y * w + gxo;
+                float *dst = Mnext + (size_t)pair * fb_m_pair_floats(h, w) + fb_m_index((unsigned)(y * w + gxo));
 #pragma unroll
-                for (int c = 0; c < 5; c++) dst[c * plane] = m[c];
+                for (int c = 0; c < 5; c++) dst[c * FB_MS] = m[c];
             }
         }
         fout += w;
@@ -720,8 +735,8 @@ int run_farneback(vqa_ctx *c, const uint8_t *gray, int npairs, int h, int w, dou
     const size_t full = (size_t)h * w;
     VQA_BUF(c, I, float, "fb.I", full * nf);
     VQA_BUF(c, R, float, "fb.R", full * 5 * nf);
-    VQA_BUF(c, M, float, "fb.M", full * 5 * npairs);
-    VQA_BUF(c, M2, float, "fb.M2", full * 5 * npairs);
+    const size_t m_pair = fb_m_pair_floats(h, w);                  // super-chunked planar M (level 0 is the largest)
+    VQA_BUF(c, M, float, "fb.M", m_pair * npairs);
     static const int fuse_epi = getenv("VQA_FB_EPI") ? atoi(getenv("VQA_FB_EPI")) : 0;
     VQA_BUF(c, flowA, float2, "fb.flowA", full * npairs);
     VQA_BUF(c, flowB, float2, "fb.flowB", full * npairs);
@@ -790,7 +805,8 @@ int run_farneback(vqa_ctx *c, const uint8_t *gray, int npairs, int h, int w, dou
             if (rows_pb < 16) rows_pb = 16;
             if (rows_pb > MS_H) rows_pb = MS_H;
         }
-        float *Mcur = M, *Mnxt = M2;
+        float *Mcur = M, *Mnxt = nullptr;
+        if (fuse_epi) { VQA_BUF(c, M2, float, "fb.M2", m_pair * npairs); Mnxt = M2; }
         const dim3 gB(cdiv(lw, MS_OUT), cdiv(lh, rows_pb), npairs);
         for (int it = 0; it < 3; it++) {
             const bool last = (k == 0 && it == 2);
