@@ -524,21 +524,26 @@ __device__ __forceinline__ void ff_add(float &hi, float &lo, float x)
     lo = __fadd_rn(lo, e);
 }
 
-// FarnebackUpdateFlow_Blur, column-marching (see above).  What bounds this kernel on B200 is the
-// number of shared-memory wavefronts and the quarter-rate XU conversions, not DRAM (ncu, profiles/):
-//   * the vertical 15-row running sums are float-float pairs updated with TwoSum on the FMA pipe (a
-//     plain float running sum would keep eps*|edge value| of error in flat areas next to strong edges;
-//     OpenCV uses double here) -- no FP64, no float<->double conversion per row;
-//   * the shared rows are 32-bit (half the wavefronts of double rows);
+// FarnebackUpdateFlow_Blur, column-marching (see above).  On B200 this kernel is bound by warp
+// instruction ISSUE (ncu: issue slots 78 % busy, 3 eligible warps per cycle; DRAM 46 %, L1 70 %), so
+// the design minimises instructions per output, in this order of discovery (profiles/r01_notes.md):
+//   * 32-bit shared rows in a conflict-free swizzle, horizontal phase on 128-bit accesses;
 //   * the horizontal 15-tap sums are plain float sums (core + suffix + prefix, no sliding window, so
 //     no error persists) with a dependent chain of 8;
-//   * only the 2x2 solve runs in double (5 + 4 conversions per output).
+//   * the 2x2 solve runs in float with FMA-recovered product errors (no conversions);
+//   * M in a layout whose plane offsets are compile-time constants (ten loads from two pointers);
+//   * VACC 1 (default): the vertical 15-row running sums are DOUBLE registers: 10 DADD + 15
+//     conversions per row.  A plain float running sum would keep eps*|edge value| of error in flat
+//     areas below strong edges (OpenCV uses double here too).  VACC 0 keeps them as float-float
+//     pairs updated with TwoSum on the FMA pipe: no XU/FP64 work but 75 FADD per row, 8 % slower
+//     now that the solve no longer loads the XU pipe (it was the faster variant before that).
 //
 // EPI 0: the new flow is stored (last iteration of a level; on level 0 the caller may ask for
-//        sum |flow| instead).  EPI 1: the flow never leaves the registers -- the UpdateMatrices of the
-//        NEXT iteration is pointwise in the pixel, so it is evaluated right here from R0/R1 and the
+//        sum |flow| instead).  EPI 1 (VQA_FB_EPI=1, off by default: 7 % slower, the gather latency of the
+//        epilogue is exposed once per row): the flow never leaves the registers -- the UpdateMatrices of
+//        the NEXT iteration is pointwise in the pixel, so it is evaluated right here from R0/R1 and the
 //        fresh flow and written to the other M buffer (saves the flow round trip and one launch).
-template <int EPI>
+template <int EPI, int VACC>
 __global__ void __launch_bounds__(MS_W)
 k_fb_blur_solve(const float *__restrict__ M, int h, int w, float2 *__restrict__ flow, int rows_per_block,
                 double *__restrict__ mag_sum, int write_flow, const float *__restrict__ R, float *__restrict__ Mnext)
@@ -552,12 +557,17 @@ k_fb_blur_solve(const float *__restrict__ M, int h, int w, float2 *__restrict__ 
     const int gx = clampi(sx0 - 8 + t, 0, w - 1);
     const int y_end = min(y0 + rows_per_block, h);
     float vh[5], vl[5];
+    double vd[5];
 #pragma unroll
-    for (int c = 0; c < 5; c++) vh[c] = vl[c] = 0.f;
+    for (int c = 0; c < 5; c++) { vh[c] = vl[c] = 0.f; vd[c] = 0.0; }
     for (int k = -MS_R; k <= MS_R; k++) {
         const float *p = src + fb_m_index((unsigned)(clampi(y0 + k, 0, h - 1) * w + gx));
 #pragma unroll
-        for (int c = 0; c < 5; c++) ff_add(vh[c], vl[c], __ldg(p + c * FB_MS));
+        for (int c = 0; c < 5; c++) {
+            const float v = __ldg(p + c * FB_MS);
+            if (VACC) vd[c] += (double)v;
+            else ff_add(vh[c], vl[c], v);
+        }
     }
     // horizontal work item: 16 lanes per plane (14 segments of 8 outputs + 2 idle lanes), so that a
     // quarter-warp of a 128-bit access never mixes planes
@@ -591,7 +601,7 @@ k_fb_blur_solve(const float *__restrict__ M, int h, int w, float2 *__restrict__ 
             yo++;
         }
 #pragma unroll
-        for (int c = 0; c < 5; c++) my_row[c * MS_VP] = __fadd_rn(vh[c], vl[c]);
+        for (int c = 0; c < 5; c++) my_row[c * MS_VP] = VACC ? (float)vd[c] : __fadd_rn(vh[c], vl[c]);
         __syncthreads();
         if (hwork) {
             // p[k] = column 8s + k; output o of the segment sums columns 8s+o+1 .. 8s+o+15
@@ -650,8 +660,12 @@ k_fb_blur_solve(const float *__restrict__ M, int h, int w, float2 *__restrict__ 
         if (more) {
 #pragma unroll
             for (int c = 0; c < 5; c++) {
-                ff_add(vh[c], vl[c], nin[c]);
-                ff_add(vh[c], vl[c], -nout[c]);
+                if (VACC) {
+                    vd[c] = (vd[c] + (double)nin[c]) - (double)nout[c];
+                } else {
+                    ff_add(vh[c], vl[c], nin[c]);
+                    ff_add(vh[c], vl[c], -nout[c]);
+                }
             }
         }
     }
@@ -738,6 +752,7 @@ int run_farneback(vqa_ctx *c, const uint8_t *gray, int npairs, int h, int w, dou
     const size_t m_pair = fb_m_pair_floats(h, w);                  // super-chunked planar M (level 0 is the largest)
     VQA_BUF(c, M, float, "fb.M", m_pair * npairs);
     static const int fuse_epi = getenv("VQA_FB_EPI") ? atoi(getenv("VQA_FB_EPI")) : 0;
+    static const int vacc = getenv("VQA_FB_VACC") ? atoi(getenv("VQA_FB_VACC")) : 1;
     VQA_BUF(c, flowA, float2, "fb.flowA", full * npairs);
     VQA_BUF(c, flowB, float2, "fb.flowB", full * npairs);
     static const int mat_v4 = getenv("VQA_MAT_V4") ? atoi(getenv("VQA_MAT_V4")) : 1;
@@ -813,13 +828,17 @@ int run_farneback(vqa_ctx *c, const uint8_t *gray, int npairs, int h, int w, dou
             if (it < 2 && fuse_epi) {
                 // blur + solve + next UpdateMatrices: M 20 + R0 20 + R1 20 read, M' 20 written
                 VQA_BYTES(c, 80.0 * lw * lh * npairs);
-                VQA_LAUNCH(c, k_fb_blur_solve<1>, gB, MS_W, 0, Mcur, lh, lw, flow, rows_pb, (double *)nullptr, 0, R, Mnxt);
+                VQA_LAUNCH(c, (k_fb_blur_solve<1, 0>), gB, MS_W, 0, Mcur, lh, lw, flow, rows_pb, (double *)nullptr, 0, R, Mnxt);
                 float *tm = Mcur; Mcur = Mnxt; Mnxt = tm;
                 continue;
             }
             VQA_BYTES(c, 28.0 * lw * lh * npairs);
-            VQA_LAUNCH(c, k_fb_blur_solve<0>, gB, MS_W, 0, Mcur, lh, lw, flow, rows_pb,
-                       last ? mag_sum : (double *)nullptr, (!last || flow_out) ? 1 : 0, (const float *)nullptr, (float *)nullptr);
+            if (vacc)
+                VQA_LAUNCH(c, (k_fb_blur_solve<0, 1>), gB, MS_W, 0, Mcur, lh, lw, flow, rows_pb,
+                           last ? mag_sum : (double *)nullptr, (!last || flow_out) ? 1 : 0, (const float *)nullptr, (float *)nullptr);
+            else
+                VQA_LAUNCH(c, (k_fb_blur_solve<0, 0>), gB, MS_W, 0, Mcur, lh, lw, flow, rows_pb,
+                           last ? mag_sum : (double *)nullptr, (!last || flow_out) ? 1 : 0, (const float *)nullptr, (float *)nullptr);
             if (it < 2) {
                 VQA_BYTES(c, 68.0 * lw * lh * npairs);
                 if ((lw & 3) == 0 && mat_v4) {
