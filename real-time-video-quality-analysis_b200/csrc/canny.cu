@@ -2,9 +2,14 @@
 //
 //   k_canny_nms     Sobel 3x3 (replicate border) + L1 magnitude (zero ring) + non-maximum
 //                   suppression with OpenCV's TG22 fixed-point sectors -> 0 / 1 (weak) / 2 (strong)
-//   k_ccl_merge     8-connected union-find over kept pixels (atomicMin on roots)
-//   k_ccl_flatten   every kept pixel points at its root; roots of components with a strong pixel get a flag bit
-//   k_ccl_count     count (and optionally paint) the kept pixels of flagged components
+//                   then connected components INSIDE the 64x16 tile (shared-memory union-find); every
+//                   kept pixel gets the global index of its tile-local root, and the tile appends its
+//                   local roots (index, pixel count, "contains a strong pixel") to a per-frame list
+//   k_ccl_merge     global union-find (atomicMin on roots) over the pixels on tile borders only
+//   k_ccl_root_flag / k_ccl_root_count   work on the list of local roots (~1 % of the pixels): flag the
+//                   global root of every local component with a strong pixel, then add up the sizes
+//                   of the local components whose global root is flagged
+//   k_ccl_flatten / k_ccl_count   per-pixel versions, only used to paint the edge map (debug tap)
 //
 // Hysteresis is a connected-components problem: the fix-point is unique, so the count equals
 // OpenCV's stack-based flood fill whatever the thread schedule.  Roofline: HBM; algorithmic
@@ -33,7 +38,7 @@ __device__ __forceinline__ void sm_union(int *L, int a, int b)
 
 __global__ void __launch_bounds__(256)
 k_canny_nms(const uint8_t *__restrict__ gray, int h, int w, int low, int high, uint8_t *__restrict__ state,
-            int *__restrict__ label)
+            int *__restrict__ label, int2 *__restrict__ roots, int *__restrict__ nroots, int roots_cap)
 {
     // Packed front end: the pixel tile is held as 32-bit words (image columns tx0-4 .. tx0+67), a work
     // item produces 4 adjacent gradient magnitudes from 6 word loads, and the NMS of 4 adjacent pixels
@@ -44,6 +49,9 @@ k_canny_nms(const uint8_t *__restrict__ gray, int h, int w, int low, int high, u
     __shared__ __align__(16) int sob[CT_H + 2][MGP];               // (dy << 16) | (dx & 0xffff)
     __shared__ __align__(4) uint8_t st[CT_H][CT_W];
     __shared__ int lab[CT_H * CT_W];                               // tile-local union-find (indices inside the tile)
+    __shared__ uint16_t sroots[CT_H * CT_W / 4];                   // local roots: at most one per 2x2 block (8-connectivity)
+    __shared__ int s_n, s_base;
+    if (threadIdx.x == 0) s_n = 0;
     const int frame = blockIdx.z;
     const uint8_t *g = gray + (size_t)frame * h * w;
     const int tx0 = blockIdx.x * CT_W, ty0 = blockIdx.y * CT_H;
@@ -139,6 +147,7 @@ k_canny_nms(const uint8_t *__restrict__ gray, int h, int w, int low, int high, u
     // run, (2) stitch runs to the row above (N, else NW / NE) with a shared-memory union-find,
     // (3) flatten and publish the GLOBAL index of the local root.  The global union-find
     // (k_ccl_merge) then only has to stitch across tile borders.
+    int *ssize = &mag[0][0], *sstrong = &sob[0][0];                // per local root: pixel count / has a strong pixel (mag, sob are dead)
     for (int i = threadIdx.x; i < CT_H * CT_W; i += 256) {
         int ty = i / CT_W, tx = i - ty * CT_W;
         int l = -1;
@@ -148,6 +157,8 @@ k_canny_nms(const uint8_t *__restrict__ gray, int h, int w, int low, int high, u
             l = ty * CT_W + x0;
         }
         lab[i] = l;
+        ssize[i] = 0;
+        sstrong[i] = 0;
     }
     __syncthreads();
     for (int i = threadIdx.x; i < CT_H * CT_W; i += 256) {
@@ -169,6 +180,17 @@ k_canny_nms(const uint8_t *__restrict__ gray, int h, int w, int low, int high, u
         int r = i;
         while (lab[r] != r) r = lab[r];
         label[(size_t)frame * h * w + (size_t)iy * w + ix] = (ty0 + r / CT_W) * w + tx0 + (r % CT_W);
+        atomicAdd(&ssize[r], 1);
+        if (st[ty][tx] == 2) sstrong[r] = 1;
+        if (r == i) sroots[atomicAdd(&s_n, 1)] = (uint16_t)i;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_n) s_base = atomicAdd(&nroots[frame], s_n);
+    __syncthreads();
+    for (int j = threadIdx.x; j < s_n; j += 256) {
+        const int i = sroots[j];
+        roots[(size_t)frame * roots_cap + s_base + j] =
+            make_int2((ty0 + i / CT_W) * w + tx0 + (i % CT_W), ssize[i] | (sstrong[i] ? (int)0x80000000 : 0));
     }
 }
 
@@ -195,29 +217,65 @@ __device__ __forceinline__ void uf_union(int *L, int a, int b)
 __global__ void __launch_bounds__(256)
 k_ccl_merge(const uint8_t *__restrict__ state, int h, int w, int *__restrict__ label)
 {
+    // one thread per pixel on a tile border: 64 of the top row, 15 + 15 of the left / right column
     const int frame = blockIdx.y;
     const uint8_t *s = state + (size_t)frame * h * w;
     int *L = label + (size_t)frame * h * w;
-    const int total = h * w;
-    for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
-        if (!s[i]) continue;
-        const int y = i / w, x = i - y * w;
-        const int tx = x % CT_W, ty = y % CT_H;
-        if (ty != 0 && tx != 0 && tx != CT_W - 1) continue;     // interior pixels were stitched inside their tile
-        if (tx == 0 && x > 0 && s[i - 1]) uf_union(L, i, i - 1);
-        if (y == 0) continue;
-        const bool north = s[i - w] != 0;
-        if (ty == 0) {                                           // row above lies in another tile
-            if (north) uf_union(L, i, i - w);
-            else {
-                if (x > 0 && s[i - w - 1]) uf_union(L, i, i - w - 1);
-                if (x < w - 1 && s[i - w + 1]) uf_union(L, i, i - w + 1);
-            }
-        } else if (!north) {                                     // only the diagonal neighbour across the side border
-            if (tx == 0 && x > 0 && s[i - w - 1]) uf_union(L, i, i - w - 1);
-            if (tx == CT_W - 1 && x < w - 1 && s[i - w + 1]) uf_union(L, i, i - w + 1);
+    const int tiles_x = (w + CT_W - 1) / CT_W, tiles = tiles_x * ((h + CT_H - 1) / CT_H);
+    const int t = blockIdx.x * 256 + threadIdx.x, tile = t / 96, k = t - tile * 96;
+    if (tile >= tiles || k >= CT_W + 2 * (CT_H - 1)) return;
+    const int ty = k < CT_W ? 0 : (k < CT_W + CT_H - 1 ? k - (CT_W - 1) : k - (CT_W + CT_H - 2));
+    const int tx = k < CT_W ? k : (k < CT_W + CT_H - 1 ? 0 : CT_W - 1);
+    const int y = (tile / tiles_x) * CT_H + ty, x = (tile % tiles_x) * CT_W + tx;
+    if (y >= h || x >= w) return;
+    const int i = y * w + x;
+    if (!s[i]) return;
+    if (tx == 0 && x > 0 && s[i - 1]) uf_union(L, i, i - 1);
+    if (y == 0) return;
+    const bool north = s[i - w] != 0;
+    if (ty == 0) {                                           // row above lies in another tile
+        if (north) uf_union(L, i, i - w);
+        else {
+            if (x > 0 && s[i - w - 1]) uf_union(L, i, i - w - 1);
+            if (x < w - 1 && s[i - w + 1]) uf_union(L, i, i - w + 1);
         }
+    } else if (!north) {                                     // only the diagonal neighbour across the side border
+        if (tx == 0 && x > 0 && s[i - w - 1]) uf_union(L, i, i - w - 1);
+        if (tx == CT_W - 1 && x < w - 1 && s[i - w + 1]) uf_union(L, i, i - w + 1);
     }
+}
+
+// local roots with a strong pixel flag their global root (a root's own entry is only ever touched by
+// atomics after the merge, so the flag survives; readers mask it)
+__global__ void __launch_bounds__(256)
+k_ccl_root_flag(const int2 *__restrict__ roots, const int *__restrict__ nroots, int roots_cap, int total, int *__restrict__ label)
+{
+    const int frame = blockIdx.y, n = nroots[frame];
+    const int2 *R = roots + (size_t)frame * roots_cap;
+    int *L = label + (size_t)frame * total;
+    for (int j = blockIdx.x * 256 + threadIdx.x; j < n; j += gridDim.x * 256) {
+        const int2 e = R[j];
+        if (e.y >= 0) continue;                                // no strong pixel in this local component
+        const int g = uf_find(L, e.x);
+        if (!(__ldcg(L + g) & LBL_FLAG)) atomicOr(&L[g], LBL_FLAG);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_ccl_root_count(const int2 *__restrict__ roots, const int *__restrict__ nroots, int roots_cap, int total,
+                 const int *__restrict__ label, unsigned long long *__restrict__ counts)
+{
+    const int frame = blockIdx.y, n = nroots[frame];
+    const int2 *R = roots + (size_t)frame * roots_cap;
+    const int *L = label + (size_t)frame * total;
+    int cnt = 0;
+    for (int j = blockIdx.x * 256 + threadIdx.x; j < n; j += gridDim.x * 256) {
+        const int2 e = R[j];
+        const int g = uf_find(L, e.x);
+        if (__ldcg(L + g) & LBL_FLAG) cnt += e.y & 0x7fffffff;
+    }
+    cnt = warp_sum(cnt);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&counts[frame], (unsigned long long)cnt);
 }
 
 // every kept pixel points at its root; roots of components that contain a strong pixel get the flag
@@ -252,7 +310,7 @@ k_ccl_count(const uint8_t *__restrict__ state, int total, const int *__restrict_
         if (edges) edges[(size_t)frame * total + i] = e ? 255 : 0;
     }
     cnt = warp_sum(cnt);
-    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&counts[frame], (unsigned long long)cnt);
+    if (counts && (threadIdx.x & 31) == 0 && cnt) atomicAdd(&counts[frame], (unsigned long long)cnt);
 }
 
 int run_canny(vqa_ctx *c, const uint8_t *gray, int n, int h, int w, unsigned long long *counts, uint8_t *edges_out)
@@ -261,19 +319,26 @@ int run_canny(vqa_ctx *c, const uint8_t *gray, int n, int h, int w, unsigned lon
     if (total > (size_t)LBL_MASK) return set_err(c, VQA_E_UNSUPPORTED, "canny: frame larger than 2^30 pixels");
     VQA_BUF(c, state, uint8_t, "canny.state", total * n);
     VQA_BUF(c, label, int, "canny.label", total * n);
+    const int tiles = cdiv(w, CT_W) * cdiv(h, CT_H), roots_cap = tiles * (CT_H * CT_W / 4);
+    VQA_BUF(c, roots, int2, "canny.roots", (size_t)roots_cap * n);
+    VQA_BUF(c, nroots, int, "canny.nroots", n);
     VQA_CUDA(c, cudaMemsetAsync(counts, 0, sizeof(unsigned long long) * (size_t)n, c->stream));
+    VQA_CUDA(c, cudaMemsetAsync(nroots, 0, sizeof(int) * (size_t)n, c->stream));
     dim3 g1(cdiv(w, CT_W), cdiv(h, CT_H), n);
     VQA_BYTES(c, 2.0 * total * n);
-    VQA_LAUNCH(c, k_canny_nms, g1, 256, 0, gray, h, w, 100, 200, state, label);
-    int bpf = cdiv((long)total, 256 * 8);
-    if (bpf < 1) bpf = 1;
-    dim3 g2(bpf, n);
-    VQA_BYTES(c, 1.0 * total * n);
-    VQA_LAUNCH(c, k_ccl_merge, g2, 256, 0, state, h, w, label);
-    VQA_BYTES(c, 1.0 * total * n);
-    VQA_LAUNCH(c, k_ccl_flatten, g2, 256, 0, state, (int)total, label);
-    VQA_BYTES(c, 1.0 * total * n);
-    VQA_LAUNCH(c, k_ccl_count, g2, 256, 0, state, (int)total, label, counts, edges_out);
+    VQA_LAUNCH(c, k_canny_nms, g1, 256, 0, gray, h, w, 100, 200, state, label, roots, nroots, roots_cap);
+    VQA_BYTES(c, 96.0 * tiles * n);
+    VQA_LAUNCH(c, k_ccl_merge, dim3(cdiv(tiles * 96, 256), n), 256, 0, state, h, w, label);
+    const dim3 gR(std::min(64, cdiv(roots_cap, 256)), n);
+    VQA_LAUNCH(c, k_ccl_root_flag, gR, 256, 0, roots, nroots, roots_cap, (int)total, label);
+    VQA_LAUNCH(c, k_ccl_root_count, gR, 256, 0, roots, nroots, roots_cap, (int)total, label, counts);
+    if (edges_out) {                                           // debug tap: paint the map with the per-pixel passes
+        int bpf = cdiv((long)total, 256 * 8);
+        if (bpf < 1) bpf = 1;
+        dim3 g2(bpf, n);
+        VQA_LAUNCH(c, k_ccl_flatten, g2, 256, 0, state, (int)total, label);
+        VQA_LAUNCH(c, k_ccl_count, g2, 256, 0, state, (int)total, label, (unsigned long long *)nullptr, edges_out);
+    }
     return VQA_OK;
 }
 

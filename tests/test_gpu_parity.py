@@ -82,11 +82,30 @@ def _canny_cases(synth):
 
 
 def test_canny_bit_exact(ctx, synth):
+    from rtvqa_b200 import _native as N
     for name, g in _canny_cases(synth):
         n, m = CO.canny_count(g, want_map=True)
         got = ctx.debug_canny(g)
         assert np.array_equal(got, m), name
         assert int((got > 0).sum()) == int(n), name
+        # the production count comes from the list of tile-local roots, not from the painted map
+        h, w = g.shape
+        bgr = np.repeat(g[..., None], 3, axis=2)[None]           # gray(v, v, v) == v
+        rows = ctx.complexity_frames(bgr, w, h, N.M_EDGE)
+        assert int(rows["edge_count"][0]) == int(n), name
+
+
+def test_canny_count_many_components(ctx):
+    """Dense salt-and-pepper: thousands of tiny components per tile row, partial border tiles."""
+    from rtvqa_b200 import _native as N
+    rng = np.random.default_rng(11)
+    for h, w in [(97, 203), (256, 320), (540, 960)]:
+        g = (rng.random((h, w)) < 0.08).astype(np.uint8) * rng.integers(40, 256, (h, w)).astype(np.uint8)
+        n = CO.canny_count(g)
+        bgr = np.repeat(g[..., None], 3, axis=2)[None]
+        rows = ctx.complexity_frames(np.concatenate([bgr, bgr[:, ::-1].copy()]), w, h, N.M_EDGE)
+        assert int(rows["edge_count"][0]) == int(n), (h, w)
+        assert int(rows["edge_count"][1]) == int(CO.canny_count(np.ascontiguousarray(g[::-1]))), (h, w)
 
 
 # ------------------------------------------------------------------ a5/a6: DCT
