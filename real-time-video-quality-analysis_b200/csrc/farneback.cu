@@ -249,91 +249,120 @@ constexpr int PE_P = 76;                         // tile pitch (64 + 2*5 = 74, p
 // shared-memory reads (vertical pass: 11 LDS.128 per 4 outputs, horizontal pass: 12 LDS.128 per 4
 // outputs).  The vertical pass is float like OpenCV's; the horizontal accumulators are double like
 // OpenCV's (ACC = double) or float (ACC = float, selectable for A/B: VQA_PE_F32=1).
+// A block walks PE_STRIP vertically adjacent tiles; the pixel tile is double-buffered and filled with
+// 4-byte cp.async (any alignment, border clamp in the address), so the loads of tile k+1 fly while
+// tile k is computed (the synchronous version sat 63 % of its stall samples on the tile load).
+constexpr int PE_STRIP = 4;
+constexpr int PE_SMEM = (2 * (PE_TH + 2 * PE_R) + 3 * PE_TH) * PE_P * (int)sizeof(float);
+
+__device__ __forceinline__ void pe_load_tile(float (*tile)[PE_P], const float *__restrict__ src, int h, int w, int tx0, int ty0, int tid)
+{
+    for (int i = tid; i < (PE_TH + 2 * PE_R) * PE_P; i += 256) {
+        const int y = i / PE_P, x = i - y * PE_P;
+        const float *g = src + (size_t)clampi(ty0 - PE_R + y, 0, h - 1) * w + clampi(tx0 - PE_R + x, 0, w - 1);
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(&tile[y][x]);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(g) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
 template <typename ACC>
 __global__ void __launch_bounds__(256)
 k_fb_polyexp(const float *__restrict__ I, int h, int w, PolyConst pc, float *__restrict__ R)
 {
-    __shared__ __align__(16) float tile[PE_TH + 2 * PE_R][PE_P];
-    __shared__ __align__(16) float v0[PE_TH][PE_P], v1[PE_TH][PE_P], v2[PE_TH][PE_P];
-    const int frame = blockIdx.z, tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+    extern __shared__ __align__(16) float pe_smem[];             // PE_SMEM bytes (> 48 KB: opt-in dynamic)
+    float (*tile)[PE_TH + 2 * PE_R][PE_P] = reinterpret_cast<float (*)[PE_TH + 2 * PE_R][PE_P]>(pe_smem);
+    float (*v0)[PE_P] = reinterpret_cast<float (*)[PE_P]>(pe_smem + 2 * (PE_TH + 2 * PE_R) * PE_P);
+    float (*v1)[PE_P] = v0 + PE_TH, (*v2)[PE_P] = v1 + PE_TH;
+    const int frame = blockIdx.z, tid = threadIdx.x;
     const float *src = I + (size_t)frame * h * w;
-    const int tx0 = blockIdx.x * PE_TW, ty0 = blockIdx.y * PE_TH;
-    for (int y = wrp; y < PE_TH + 2 * PE_R; y += 8) {
-        const float *g = src + (size_t)clampi(ty0 - PE_R + y, 0, h - 1) * w;
-        for (int x = lane; x < PE_P; x += 32) tile[y][x] = __ldg(g + clampi(tx0 - PE_R + x, 0, w - 1));
-    }
-    __syncthreads();
-    for (int i = tid; i < PE_TH * (PE_P / 4); i += 256) {
-        const int y = i / (PE_P / 4), x = (i - y * (PE_P / 4)) * 4;
-        const float4 c4 = *reinterpret_cast<const float4 *>(&tile[y + PE_R][x]);
-        float t0[4] = {c4.x * pc.g[PE_R], c4.y * pc.g[PE_R], c4.z * pc.g[PE_R], c4.w * pc.g[PE_R]};
-        float t1[4] = {0.f, 0.f, 0.f, 0.f}, t2[4] = {0.f, 0.f, 0.f, 0.f};
+    const int tx0 = blockIdx.x * PE_TW;
+    const int tiles_y = (h + PE_TH - 1) / PE_TH, k0 = blockIdx.y * PE_STRIP, nk = min(PE_STRIP, tiles_y - k0);
+    const size_t plane = (size_t)h * w;
+    const int x4 = (tid & 15) * 4, gx0 = tx0 + x4;
+    pe_load_tile(tile[0], src, h, w, tx0, k0 * PE_TH, tid);
+    for (int kt = 0; kt < nk; kt++) {
+        const int ty0 = (k0 + kt) * PE_TH;
+        float (*T)[PE_P] = tile[kt & 1];
+        if (kt + 1 < nk) {
+            pe_load_tile(tile[(kt + 1) & 1], src, h, w, tx0, ty0 + PE_TH, tid);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        for (int i = tid; i < PE_TH * (PE_P / 4); i += 256) {
+            const int y = i / (PE_P / 4), x = (i - y * (PE_P / 4)) * 4;
+            const float4 c4 = *reinterpret_cast<const float4 *>(&T[y + PE_R][x]);
+            float t0[4] = {c4.x * pc.g[PE_R], c4.y * pc.g[PE_R], c4.z * pc.g[PE_R], c4.w * pc.g[PE_R]};
+            float t1[4] = {0.f, 0.f, 0.f, 0.f}, t2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int k = 1; k <= PE_R; k++) {
-            const float4 a4 = *reinterpret_cast<const float4 *>(&tile[y + PE_R - k][x]);
-            const float4 b4 = *reinterpret_cast<const float4 *>(&tile[y + PE_R + k][x]);
-            const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+            for (int k = 1; k <= PE_R; k++) {
+                const float4 a4 = *reinterpret_cast<const float4 *>(&T[y + PE_R - k][x]);
+                const float4 b4 = *reinterpret_cast<const float4 *>(&T[y + PE_R + k][x]);
+                const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const float p = a[j] + b[j];
-                t0[j] = t0[j] + pc.g[PE_R + k] * p;
-                t1[j] = t1[j] + pc.xg[PE_R + k] * (b[j] - a[j]);
-                t2[j] = t2[j] + pc.xxg[PE_R + k] * p;
+                for (int j = 0; j < 4; j++) {
+                    const float p = a[j] + b[j];
+                    t0[j] = t0[j] + pc.g[PE_R + k] * p;
+                    t1[j] = t1[j] + pc.xg[PE_R + k] * (b[j] - a[j]);
+                    t2[j] = t2[j] + pc.xxg[PE_R + k] * p;
+                }
+            }
+            *reinterpret_cast<float4 *>(&v0[y][x]) = make_float4(t0[0], t0[1], t0[2], t0[3]);
+            *reinterpret_cast<float4 *>(&v1[y][x]) = make_float4(t1[0], t1[1], t1[2], t1[3]);
+            *reinterpret_cast<float4 *>(&v2[y][x]) = make_float4(t2[0], t2[1], t2[2], t2[3]);
+        }
+        __syncthreads();
+        if (gx0 < w) {
+            for (int y = tid >> 4; y < PE_TH; y += 16) {
+                const int gy = ty0 + y;
+                if (gy >= h) break;
+                float a0[16], a1[16], a2[16];                 // columns x4 .. x4+15 of the three vertical results
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const float4 p0 = *reinterpret_cast<const float4 *>(&v0[y][x4 + 4 * q]);
+                    const float4 p1 = *reinterpret_cast<const float4 *>(&v1[y][x4 + 4 * q]);
+                    const float4 p2 = *reinterpret_cast<const float4 *>(&v2[y][x4 + 4 * q]);
+                    a0[4 * q] = p0.x; a0[4 * q + 1] = p0.y; a0[4 * q + 2] = p0.z; a0[4 * q + 3] = p0.w;
+                    a1[4 * q] = p1.x; a1[4 * q + 1] = p1.y; a1[4 * q + 2] = p1.z; a1[4 * q + 3] = p1.w;
+                    a2[4 * q] = p2.x; a2[4 * q + 1] = p2.y; a2[4 * q + 2] = p2.z; a2[4 * q + 3] = p2.w;
+                }
+                float o[5][4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int c = j + PE_R;
+                    const ACC g0 = pc.g[PE_R];
+                    ACC b1 = a0[c] * g0, b2 = 0, b3 = a1[c] * g0, b4 = 0, b5 = a2[c] * g0, b6 = 0;
+#pragma unroll
+                    for (int k = 1; k <= PE_R; k++) {
+                        const ACC gk = pc.g[PE_R + k], xgk = pc.xg[PE_R + k], xxgk = pc.xxg[PE_R + k];
+                        const ACC tg = (ACC)(a0[c + k] + a0[c - k]);
+                        b1 += tg * gk;
+                        b4 += tg * xxgk;
+                        b2 += (ACC)(a0[c + k] - a0[c - k]) * xgk;
+                        b3 += (ACC)(a1[c + k] + a1[c - k]) * gk;
+                        b6 += (ACC)(a1[c + k] - a1[c - k]) * xgk;
+                        b5 += (ACC)(a2[c + k] + a2[c - k]) * gk;
+                    }
+                    o[0][j] = (float)(b3 * (ACC)pc.ig11);
+                    o[1][j] = (float)(b2 * (ACC)pc.ig11);
+                    o[2][j] = (float)(b1 * (ACC)pc.ig03 + b5 * (ACC)pc.ig33);
+                    o[3][j] = (float)(b1 * (ACC)pc.ig03 + b4 * (ACC)pc.ig33);
+                    o[4][j] = (float)(b6 * (ACC)pc.ig55);
+                }
+                float *dst = R + (size_t)frame * 5 * plane + (size_t)gy * w + gx0;
+                const bool vec = (w & 3) == 0 && gx0 + 4 <= w;          // planes are 256-byte aligned, w % 4 == 0 keeps rows aligned
+#pragma unroll
+                for (int ch = 0; ch < 5; ch++) {
+                    if (vec) *reinterpret_cast<float4 *>(dst + ch * plane) = make_float4(o[ch][0], o[ch][1], o[ch][2], o[ch][3]);
+                    else
+                        for (int j = 0; j < 4; j++)
+                            if (gx0 + j < w) dst[ch * plane + j] = o[ch][j];
+                }
             }
         }
-        *reinterpret_cast<float4 *>(&v0[y][x]) = make_float4(t0[0], t0[1], t0[2], t0[3]);
-        *reinterpret_cast<float4 *>(&v1[y][x]) = make_float4(t1[0], t1[1], t1[2], t1[3]);
-        *reinterpret_cast<float4 *>(&v2[y][x]) = make_float4(t2[0], t2[1], t2[2], t2[3]);
-    }
-    __syncthreads();
-    const int x4 = (tid & 15) * 4, gx0 = tx0 + x4;
-    if (gx0 >= w) return;
-    const size_t plane = (size_t)h * w;
-    for (int y = tid >> 4; y < PE_TH; y += 16) {
-    const int gy = ty0 + y;
-    if (gy >= h) break;
-    float a0[16], a1[16], a2[16];                 // columns x4 .. x4+15 of the three vertical results
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-        const float4 p0 = *reinterpret_cast<const float4 *>(&v0[y][x4 + 4 * q]);
-        const float4 p1 = *reinterpret_cast<const float4 *>(&v1[y][x4 + 4 * q]);
-        const float4 p2 = *reinterpret_cast<const float4 *>(&v2[y][x4 + 4 * q]);
-        a0[4 * q] = p0.x; a0[4 * q + 1] = p0.y; a0[4 * q + 2] = p0.z; a0[4 * q + 3] = p0.w;
-        a1[4 * q] = p1.x; a1[4 * q + 1] = p1.y; a1[4 * q + 2] = p1.z; a1[4 * q + 3] = p1.w;
-        a2[4 * q] = p2.x; a2[4 * q + 1] = p2.y; a2[4 * q + 2] = p2.z; a2[4 * q + 3] = p2.w;
-    }
-    float o[5][4];
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        const int c = j + PE_R;
-        const ACC g0 = pc.g[PE_R];
-        ACC b1 = a0[c] * g0, b2 = 0, b3 = a1[c] * g0, b4 = 0, b5 = a2[c] * g0, b6 = 0;
-#pragma unroll
-        for (int k = 1; k <= PE_R; k++) {
-            const ACC gk = pc.g[PE_R + k], xgk = pc.xg[PE_R + k], xxgk = pc.xxg[PE_R + k];
-            const ACC tg = (ACC)(a0[c + k] + a0[c - k]);
-            b1 += tg * gk;
-            b4 += tg * xxgk;
-            b2 += (ACC)(a0[c + k] - a0[c - k]) * xgk;
-            b3 += (ACC)(a1[c + k] + a1[c - k]) * gk;
-            b6 += (ACC)(a1[c + k] - a1[c - k]) * xgk;
-            b5 += (ACC)(a2[c + k] + a2[c - k]) * gk;
-        }
-        o[0][j] = (float)(b3 * (ACC)pc.ig11);
-        o[1][j] = (float)(b2 * (ACC)pc.ig11);
-        o[2][j] = (float)(b1 * (ACC)pc.ig03 + b5 * (ACC)pc.ig33);
-        o[3][j] = (float)(b1 * (ACC)pc.ig03 + b4 * (ACC)pc.ig33);
-        o[4][j] = (float)(b6 * (ACC)pc.ig55);
-    }
-    float *dst = R + (size_t)frame * 5 * plane + (size_t)gy * w + gx0;
-    const bool vec = (w & 3) == 0 && gx0 + 4 <= w;          // planes are 256-byte aligned, w % 4 == 0 keeps rows aligned
-#pragma unroll
-    for (int ch = 0; ch < 5; ch++) {
-        if (vec) *reinterpret_cast<float4 *>(dst + ch * plane) = make_float4(o[ch][0], o[ch][1], o[ch][2], o[ch][3]);
-        else
-            for (int j = 0; j < 4; j++)
-                if (gx0 + j < w) dst[ch * plane + j] = o[ch][j];
-    }
+        __syncthreads();                                     // v0..v2 and this tile buffer are rewritten next round
     }
 }
 
@@ -797,8 +826,14 @@ int run_farneback(vqa_ctx *c, const uint8_t *gray, int npairs, int h, int w, dou
             }
         }
         VQA_BYTES(c, 24.0 * lw * lh * nf);
-        if (pe_f32) VQA_LAUNCH(c, k_fb_polyexp<float>, dim3(cdiv(lw, PE_TW), cdiv(lh, PE_TH), nf), 256, 0, I, lh, lw, pc, R);
-        else VQA_LAUNCH(c, k_fb_polyexp<double>, dim3(cdiv(lw, PE_TW), cdiv(lh, PE_TH), nf), 256, 0, I, lh, lw, pc, R);
+        const dim3 gE(cdiv(lw, PE_TW), cdiv(cdiv(lh, PE_TH), PE_STRIP), nf);
+        if (pe_f32) {
+            VQA_CUDA(c, cudaFuncSetAttribute(k_fb_polyexp<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, PE_SMEM));
+            VQA_LAUNCH(c, k_fb_polyexp<float>, gE, 256, PE_SMEM, I, lh, lw, pc, R);
+        } else {
+            VQA_CUDA(c, cudaFuncSetAttribute(k_fb_polyexp<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, PE_SMEM));
+            VQA_LAUNCH(c, k_fb_polyexp<double>, gE, 256, PE_SMEM, I, lh, lw, pc, R);
+        }
         const bool v4 = (lw & 3) == 0 && mat_v4;
         const dim3 gV(cdiv(lw, 128), cdiv(lh, 8), npairs);
         if (k == levels) {
