@@ -465,7 +465,7 @@ int run_dct_umma(vqa_ctx *c, const uint8_t *x, int n, int h, int w, float *coef,
     // N tile per GEMM (measured, 48 x 1080p): GEMM 1 with BN = 256 (3 stages of 64 KB) runs at
     // 1356 TFLOP/s issued vs 1110 with BN = 128; GEMM 2 with BN = 256 has room for 2 stages only
     // (96 KB each) and is no faster than BN = 128 with 3 stages (1097 vs 1128 TFLOP/s).
-    constexpr int BN1 = 256, BN2 = 128;
+    constexpr int BN1 = 256, BN2 = 128;      // BN2 = 256 (2 smem stages of 96 KB) measured 4 % slower
     UmmaState *s;
     int rc = get_state(c, &s);
     if (rc) return rc;
