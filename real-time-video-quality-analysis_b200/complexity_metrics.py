@@ -22,8 +22,10 @@ import numpy as np
 
 try:
     from . import _native as N
+    from .frame_source import SampledFrameSource
 except ImportError:  # used as a top-level drop-in module (package dir on sys.path)
     import _native as N  # type: ignore
+    from frame_source import SampledFrameSource  # type: ignore
 
 logging.basicConfig(level=logging.INFO)
 logger = logging.getLogger(__name__)
@@ -285,22 +287,42 @@ def calculate_temporal_dct(video_path, resize_width, resize_height, frame_interv
     return _smoothed_mean(r["temporal_dct"][1:], smoothing_factor, empty=0.0)
 
 
+STREAM_CHUNK_FRAMES = 48      # sampled frames per decode chunk (= the device chunk of vqa_complexity_frames)
+
+
+def stream_clip_metrics(video_path, resize_width, resize_height, frame_interval=10, chunk_frames=None, mask=N.M_ALL):
+    """Single-decode streaming analysis of a clip.  Decodes in a background thread,
+    pushes chunks of sampled frames through the device with the previous chunk's last frame as
+    halo, and returns ``(rows, timestamps)``: one FRAME_DTYPE row per sampled frame ``s_0 .. s_{K-1}``
+    (``None`` if the clip yields no sampled frame) and the reference's timestamp list (ms of source
+    frames 0, I, 2I, ...).  Results are identical to analysing the fully decoded clip in one call."""
+    validate_video_path(video_path)
+    src = SampledFrameSource(video_path, frame_interval, chunk_frames or STREAM_CHUNK_FRAMES)
+    ctx, parts, halo = None, [], None
+    for chunk in src:
+        if ctx is None:
+            ctx = N.get_context()
+        parts.append(ctx.complexity_frames(chunk, resize_width, resize_height, mask, halo=halo))
+        halo = chunk[-1]
+    rows = np.concatenate(parts) if parts else None
+    return rows, list(src.timestamps)
+
+
 def calculate_average_scene_complexity(video_path, resize_width, resize_height, frame_interval=10,
                                        smoothing_factor=0.8, num_workers=None, batch_size=100):
     """Reference :246-310.  Returns, in the reference's order, the means of the EWM-smoothed
-    series of: motion, dct, histogram, edge, orb, colour histogram, temporal dct, framerate."""
-    frame_pairs = read_frame_pairs(video_path, frame_interval)
+    series of: motion, dct, histogram, edge, orb, colour histogram, temporal dct, framerate.
+    One decode of the file (the reference makes three) feeds every metric and the timestamps."""
     if num_workers is None:
         num_workers = multiprocessing.cpu_count() // 2      # accepted for API compatibility
     a = smoothing_factor
-    clip = _stack_sampled(frame_pairs)
-    if clip is None:
+    r, frame_timestamps = stream_clip_metrics(video_path, resize_width, resize_height, frame_interval)
+    if r is None or len(r) < 2:                              # fewer than one (current, previous) pair
         nan = np.float64("nan")
         motion = dct = hist = edge = orb = color = nan
         tdct = 0.0
     else:
-        logger.info("Calculating all scene-complexity metrics on the GPU (%d sampled frames)...", len(clip))
-        r = _clip_metrics(clip, resize_width, resize_height, batch_size)
+        logger.info("Calculated all scene-complexity metrics on the GPU (%d sampled frames)", len(r))
         # per-frame metrics use pair[0] only: s_1..s_{K-1} (reference :271); s_0 is never analysed
         motion = _smoothed_mean(r["motion"][1:], a)
         dct = _smoothed_mean(r["dct_energy"][1:], a)
@@ -309,7 +331,6 @@ def calculate_average_scene_complexity(video_path, resize_width, resize_height, 
         orb = _smoothed_mean(r["orb_count"][1:], a)
         color = _smoothed_mean(r["color_entropy"][1:], a)
         tdct = _smoothed_mean(r["temporal_dct"][2:], a, empty=0.0)
-    frame_timestamps = extract_frame_timestamps(video_path, frame_interval)
     fps = N.get_context().framerate_series(frame_timestamps) if len(frame_timestamps) > 1 else []
     framerate = _smoothed_mean(fps, a)
     return (motion, dct, hist, edge, orb, color, tdct, framerate)

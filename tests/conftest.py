@@ -37,3 +37,4 @@ def vqa():
 def synth():
     import rtvqa_b200
     return rtvqa_b200.synth
+

@@ -342,6 +342,11 @@ def test_series_stats(ctx, golden):
 
 
 # ------------------------------------------------------------------ the reference-shaped API
+def conftest_fake_capture(frames, fps):
+    from helpers import FakeCapture
+    return FakeCapture(frames, fps)
+
+
 def test_drop_in_api_matches_reference_outputs(vqa, golden, small_clip, monkeypatch):
     """calculate_average_scene_complexity / process_in_batches with the reference's signatures;
     readers patched exactly as oracle/make_golden.py patches the reference's."""
@@ -359,6 +364,11 @@ def test_drop_in_api_matches_reference_outputs(vqa, golden, small_clip, monkeypa
 
     monkeypatch.setattr(cm, "read_frame_pairs", read_frame_pairs)
     monkeypatch.setattr(cm, "extract_frame_timestamps", extract_frame_timestamps)
+    # calculate_average_scene_complexity decodes once through SampledFrameSource: serve the same clip
+    # through a VideoCapture stand-in (POS_MSEC of the frame just read = 1000 * k / fps)
+    from rtvqa_b200.frame_source import SampledFrameSource
+    monkeypatch.setattr(cm, "SampledFrameSource", functools.partial(
+        SampledFrameSource, capture_factory=lambda path: conftest_fake_capture(small_clip, 30.0)))
     for key, rw, rh, interval in (("small_avg_i1_64", 64, 64, 1), ("small_avg_i3_64", 64, 64, 3),
                                   ("small_avg_i1_native", 128, 96, 1)):
         got = cm.calculate_average_scene_complexity("synthetic.mp4", rw, rh, frame_interval=interval)
@@ -388,3 +398,33 @@ def test_drop_in_api_matches_reference_outputs(vqa, golden, small_clip, monkeypa
     with pytest.raises(TypeError):
         cm.process_in_batches(frames, lambda f: 0, 2)
     assert cm.process_frame_interval_for_parallel((0.0, 1000.0 / 30.0)) == pytest.approx(30.0)
+
+
+# ------------------------------------------------------------------ f1: single-decode streaming source
+def test_streaming_clip_equals_whole_clip(vqa, ctx, small_clip, tmp_path):
+    """stream_clip_metrics (one decode, chunks + halo, decode thread) == the whole decoded clip in one call."""
+    cv2 = pytest.importorskip("cv2")
+    from rtvqa_b200 import complexity_metrics as cm
+    path = str(tmp_path / "clip.avi")
+    h, w = small_clip.shape[1:3]
+    wr = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"MJPG"), 30.0, (w, h))
+    if not wr.isOpened():
+        pytest.skip("no MJPG writer in this OpenCV build")
+    for f in small_clip:
+        wr.write(f)
+    wr.release()
+    for interval, chunk in ((1, 7), (3, 2)):
+        pairs = cm.read_frame_pairs(path, interval)
+        clip = np.stack([pairs[0][1]] + [p[0] for p in pairs])
+        whole = ctx.complexity_frames(clip, 64, 64)
+        rows, stamps = cm.stream_clip_metrics(path, 64, 64, interval, chunk_frames=chunk)
+        assert len(rows) == len(whole) and stamps == cm.extract_frame_timestamps(path, interval)
+        for name in ("edge_count", "orb_count", "gray_sq_sum"):
+            assert np.array_equal(rows[name], whole[name]), name
+        for name in ("hist_entropy", "color_entropy", "dct_energy"):
+            np.testing.assert_allclose(rows[name], whole[name], rtol=1e-6, err_msg=name)
+        np.testing.assert_allclose(rows["motion"][1:], whole["motion"][1:], rtol=1e-6)
+        np.testing.assert_allclose(rows["temporal_dct"][1:], whole["temporal_dct"][1:], rtol=1e-6)
+        got = cm.calculate_average_scene_complexity(path, 64, 64, frame_interval=interval)
+        assert all(isinstance(v, np.float64) and np.isfinite(v) for v in got)
+    assert all(np.isnan(v) for v in cm.calculate_average_scene_complexity(str(tmp_path / "missing.mp4"), 64, 64)[:6])
