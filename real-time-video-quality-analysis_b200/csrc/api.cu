@@ -1,6 +1,7 @@
 // extern "C" entry points of libvqa_b200.so (include/vqa_b200.h): context, scratch arena, the
 // chunked/double-buffered clip pipeline and the stage-level debug taps.
 #include <chrono>
+#include <vector>
 #include <math.h>
 #include <stdarg.h>
 #include <stdlib.h>
@@ -357,10 +358,24 @@ int complexity_impl(vqa_ctx *c, const uint8_t *bgr, int n, int h, int w, size_t 
         VQA_BUF(c, in2, uint8_t, "in.bgr2", FB * CH);
         in[0] = in0; in[1] = in1; in[2] = in2;
     }
-    const int nchunks = cdiv(n, CH);
+    // Chunk schedule.  Device-resident input: equal chunks of CH frames.  Host input: the first chunk is
+    // small and the sizes grow by ~1.3x up to CH, so the compute stream starts after the copy of 8 frames
+    // instead of 48 (5 ms of a 95 ms clip) and every following copy still hides behind the previous chunk.
+    std::vector<int> cstart;
+    {
+        static const int ramp0 = getenv("VQA_RAMP0") ? atoi(getenv("VQA_RAMP0")) : 8;
+        int pos = 0, sz = (!on_device && ramp0 > 0) ? std::min(CH, ramp0) : CH;
+        while (pos < n) {
+            cstart.push_back(pos);
+            pos += sz;
+            sz = std::min(CH, (sz * 4 + 2) / 3);
+        }
+        cstart.push_back(n);
+    }
+    const int nchunks = (int)cstart.size() - 1;
     static const bool use_side = !(getenv("VQA_SIDE_STREAM") && atoi(getenv("VQA_SIDE_STREAM")) == 0);
     auto h2d_chunk = [&](int ci) -> int {
-        const int s = ci * CH, m = std::min(CH, n - s);
+        const int s = cstart[ci], m = cstart[ci + 1] - s;
         if (frame_stride == FB) {
             VQA_CUDA(c, cudaMemcpyAsync(in[ci % 3], bgr + (size_t)s * frame_stride, FB * m, cudaMemcpyHostToDevice, c->copy_stream));
         } else {
@@ -398,7 +413,7 @@ int complexity_impl(vqa_ctx *c, const uint8_t *bgr, int n, int h, int w, size_t 
         has_prev = true;
     }
     for (int ci = 0; ci < nchunks; ci++) {
-        const int s = ci * CH, m = std::min(CH, n - s);
+        const int s = cstart[ci], m = cstart[ci + 1] - s;
         const uint8_t *src;
         size_t stride;
         if (on_device) {
@@ -410,8 +425,8 @@ int complexity_impl(vqa_ctx *c, const uint8_t *bgr, int n, int h, int w, size_t 
                 if (ci >= 2) VQA_CUDA(c, cudaEventSynchronize(c->ev_done[(ci + 1) % 3]));   // chunk ci-2 released the slot
                 if ((rc = h2d_chunk(ci + 1))) return rc;
             }
-            if (side && nchunks > 0)                      // a slice of the side load behind the next chunk's copy
-                if ((rc = side_issue(c, side, side->total / nchunks + 1))) return rc;
+            if (side)                                     // a slice of the side load (proportional to the chunk) behind the next chunk's copy
+                if ((rc = side_issue(c, side, (size_t)((double)side->total * m / n) + 1))) return rc;
             src = in[ci % 3];
             stride = FB;
         }
