@@ -214,8 +214,9 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"           # keep stdout to the single JSON line
+        # stdout carries the single JSON line: NCCL's own log (its "NCCL version ..." banner is printed at
+        # every level from VERSION up, INFO traces when the operator asks for them) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     ctx = N.get_context(local)
     ctx.use_torch_stream()

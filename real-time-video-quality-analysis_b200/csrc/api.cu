@@ -306,7 +306,26 @@ int side_issue(vqa_ctx *c, SideLoad *s, size_t budget)
     return VQA_OK;
 }
 
+int complexity_body(vqa_ctx *c, const uint8_t *bgr, int n, int h, int w, size_t frame_stride, const uint8_t *halo,
+                    int on_device, const vqa_cfg *cfg, vqa_frame_metrics *out, SideLoad *side);
+
+// An error can leave the chunk pipeline half enqueued (side stream forked and not joined, copies in
+// flight into the staging slots): drain all three streams before handing the context back, so the next
+// call starts from a quiescent state and the caller may free its buffers.
 int complexity_impl(vqa_ctx *c, const uint8_t *bgr, int n, int h, int w, size_t frame_stride, const uint8_t *halo,
+                    int on_device, const vqa_cfg *cfg, vqa_frame_metrics *out, SideLoad *side)
+{
+    const int rc = complexity_body(c, bgr, n, h, w, frame_stride, halo, on_device, cfg, out, side);
+    if (rc != VQA_OK && c) {
+        if (c->side_stream) cudaStreamSynchronize(c->side_stream);
+        if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+        if (c->stream) cudaStreamSynchronize(c->stream);
+        cudaGetLastError();                                  // the error is already recorded in c->err
+    }
+    return rc;
+}
+
+int complexity_body(vqa_ctx *c, const uint8_t *bgr, int n, int h, int w, size_t frame_stride, const uint8_t *halo,
                     int on_device, const vqa_cfg *cfg, vqa_frame_metrics *out, SideLoad *side)
 {
     if (!c) return VQA_E_INVALID;
