@@ -192,7 +192,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
     return 0
 
 
@@ -384,14 +384,35 @@ def run_b200(args):
             "result": {"scene_complexity": [float(v) for v in res], "psnr_avg_first": float(fr["psnr_avg"][0]),
                        "ssim_all_first": float(fr["ssim_all"][0])},
         }
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
 
 
+_JSON_OUT = None
+
+
+def _claim_stdout():
+    """stdout must carry exactly one JSON line, but libraries write to fd 1 behind Python's back (NCCL
+    prints its version banner with plain printf at NCCL_DEBUG=VERSION/WARN).  Keep a private handle on
+    the real stdout for the JSON line and point fd 1 at stderr for everything else."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
