@@ -107,3 +107,82 @@ def sharded_average_scene_complexity(local_frames, a: int, k_frames: int, resize
     fps = ctx.framerate_series(timestamps_ms) if len(timestamps_ms) > 1 else np.zeros(0)
     fr = ctx.ewm_partial(fps, 0, len(fps), alpha) if len(fps) else float("nan")
     return finalize(partials, k_frames, fr), ints
+
+
+# --------------------------------------------------------------------------- many clips (BASELINE config 5)
+def plan_clip_shards(clip_frames, world: int):
+    """"shard by clip first, then by frame range inside a clip if clips < GPUs".
+
+    clip_frames  sampled-frame count K_c of every clip
+    returns      per rank, a list of (clip, a, b): sampled frames [a, b) of that clip.
+
+    clips >= ranks: whole clips, longest first onto the least loaded rank (no halo anywhere).
+    clips <  ranks: every clip gets a group of ranks in proportion to its length (at least one) and is
+    cut into contiguous ranges inside the group (one halo frame per cut).  Deterministic, so every
+    rank computes the same plan without communication."""
+    n = len(clip_frames)
+    plan = [[] for _ in range(world)]
+    if n == 0:
+        return plan
+    if n >= world:
+        load = [0] * world
+        for c in sorted(range(n), key=lambda i: (-clip_frames[i], i)):
+            r = min(range(world), key=lambda j: (load[j], j))
+            plan[r].append((c, 0, int(clip_frames[c])))
+            load[r] += int(clip_frames[c])
+        for p in plan:
+            p.sort()
+        return plan
+    total = float(sum(clip_frames)) or 1.0
+    ranks = [1] * n
+    for _ in range(world - n):                       # hand out the spare ranks to the clip with the most frames per rank
+        c = max(range(n), key=lambda i: (clip_frames[i] / ranks[i], -i))
+        ranks[c] += 1
+    r0 = 0
+    for c in range(n):
+        for j in range(ranks[c]):
+            a, b = shard_range(int(clip_frames[c]), j, ranks[c])
+            if b > a:
+                plan[r0 + j].append((c, a, b))
+        r0 += ranks[c]
+    return plan
+
+
+def multi_clip_partials(plan_for_rank, rows_of, clip_frames, alpha: float, partial_fn):
+    """[n_clips, 7] weighted partial sums and [n_clips, 3] integer totals (edges, ORB keypoints, frames)
+    of this rank's shards.  ``rows_of(clip, a, b)`` returns the FRAME_DTYPE rows of sampled frames
+    [a, b) of ``clip`` (pair metrics of row 0 against frame a-1 when a > 0)."""
+    n = len(clip_frames)
+    partials = np.zeros((n, len(SERIES)), dtype=np.float64)
+    ints = np.zeros((n, 3), dtype=np.int64)
+    for clip, a, b in plan_for_rank:
+        rows = rows_of(clip, a, b)
+        partials[clip] += local_partials(rows, a, int(clip_frames[clip]), alpha, partial_fn)
+        lo = max(1 - a, 0)
+        ints[clip] += (int(rows["edge_count"][lo:].sum()), int(rows["orb_count"][lo:].sum()), len(rows))
+    return partials, ints
+
+
+def sharded_multi_clip_scene_complexity(clips, resize_width: int, resize_height: int, timestamps_ms, rank: int, world: int,
+                                        alpha: float = 0.8, group=None, ctx=None):
+    """All clips of a batch over all ranks: ONE all-reduce of [n_clips x 7] doubles (+ [n_clips x 3]
+    integers) closes every clip.  ``clips[c]`` is the (K_c,h,w,3) uint8 array (host or CUDA tensor) of
+    sampled frames -- only the shards of ``plan_clip_shards(...)[rank]`` are touched, so a rank may
+    pass ``None`` for clips it does not own.  Returns a list of 8-tuples in the reference's order."""
+    from . import _native as N
+    ctx = ctx or N.get_context()
+    clip_frames = [len(t) for t in timestamps_ms]
+    plan = plan_clip_shards(clip_frames, world)[rank]
+
+    def rows_of(clip, a, b):
+        fr = clips[clip]
+        return ctx.complexity_frames(fr[a:b], resize_width, resize_height, N.M_ALL, halo=fr[a - 1] if a > 0 else None)
+
+    partials, ints = multi_clip_partials(plan, rows_of, clip_frames, alpha, ctx.ewm_partial)
+    partials, ints = reduce_partials(partials, ints, group)
+    out = []
+    for c, ts in enumerate(timestamps_ms):
+        fps = ctx.framerate_series(ts) if len(ts) > 1 else np.zeros(0)
+        fr = ctx.ewm_partial(fps, 0, len(fps), alpha) if len(fps) else float("nan")
+        out.append(finalize(partials[c], clip_frames[c], fr))
+    return out, ints

@@ -428,3 +428,29 @@ def test_streaming_clip_equals_whole_clip(vqa, ctx, small_clip, tmp_path):
         got = cm.calculate_average_scene_complexity(path, 64, 64, frame_interval=interval)
         assert all(isinstance(v, np.float64) and np.isfinite(v) for v in got)
     assert all(np.isnan(v) for v in cm.calculate_average_scene_complexity(str(tmp_path / "missing.mp4"), 64, 64)[:6])
+
+
+def test_multi_clip_sharding_on_device(vqa, ctx, small_clip):
+    """BASELINE config 5 shape (many clips): the batched call equals the per-clip call, and a 3-rank
+    plan evaluated rank by rank on this GPU sums to the same partials."""
+    from rtvqa_b200 import _native as N
+    from rtvqa_b200 import sharding as SH
+    clips = [small_clip[:10], small_clip[10:16], small_clip[16:17]]
+    ts = [list(1000.0 * np.arange(len(c)) / 30.0) for c in clips]
+    got, ints = SH.sharded_multi_clip_scene_complexity(clips, 64, 64, ts, rank=0, world=1, ctx=ctx)
+    for c, clip in enumerate(clips):
+        one, one_ints = SH.sharded_average_scene_complexity(clip, 0, len(clip), 64, 64, ts[c], ctx=ctx)
+        np.testing.assert_allclose(got[c], one, rtol=1e-12, equal_nan=True)
+        assert list(ints[c]) == list(one_ints)
+    lens = [len(c) for c in clips]
+
+    def rows_of(clip, a, b):
+        fr = clips[clip]
+        return ctx.complexity_frames(fr[a:b], 64, 64, N.M_ALL, halo=fr[a - 1] if a > 0 else None)
+
+    plan = SH.plan_clip_shards(lens, 5)                            # 3 clips over 5 ranks: the long clip is cut
+    assert sum(len(p) for p in plan) > len(clips)
+    parts = [SH.multi_clip_partials(plan[r], rows_of, lens, 0.8, ctx.ewm_partial) for r in range(5)]
+    whole = SH.multi_clip_partials(SH.plan_clip_shards(lens, 1)[0], rows_of, lens, 0.8, ctx.ewm_partial)
+    np.testing.assert_allclose(sum(p for p, _ in parts), whole[0], rtol=1e-6)
+    assert np.array_equal(sum(i for _, i in parts), whole[1])

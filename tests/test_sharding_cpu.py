@@ -107,3 +107,55 @@ def test_empty_series_conventions(vqa):
     assert all(np.isnan(v) for v in res[:6]) and res[6] == 0.0 and np.isnan(res[7])
     res = SH.finalize(np.ones(len(SH.SERIES)), 2, 3.0)                 # two frames: temporal DCT still empty -> 0.0
     assert res[0] == 1.0 and res[6] == 0.0 and res[7] == 3.0
+
+
+# ------------------------------------------------------------------ many clips (BASELINE config 5)
+@pytest.mark.parametrize("clip_frames,world", [([600] * 64, 8), ([600, 300, 900, 120, 60], 2), ([30, 10], 8),
+                                               ([299], 8), ([5, 0, 7], 4), ([], 4), ([3], 8)])
+def test_clip_shard_plan_covers_every_frame_once(vqa, clip_frames, world):
+    from rtvqa_b200 import sharding as SH
+    plan = SH.plan_clip_shards(clip_frames, world)
+    assert len(plan) == world
+    seen = {c: [] for c in range(len(clip_frames))}
+    for shards in plan:
+        for c, a, b in shards:
+            assert 0 <= a < b <= clip_frames[c]
+            seen[c].append((a, b))
+    for c, k in enumerate(clip_frames):
+        rs = sorted(seen[c])
+        assert sum(b - a for a, b in rs) == k
+        assert all(rs[i][1] == rs[i + 1][0] for i in range(len(rs) - 1)) and (not rs or (rs[0][0] == 0 and rs[-1][1] == k))
+    if len(clip_frames) >= world:                                  # whole clips only: no halo needed anywhere
+        assert all(a == 0 and b == clip_frames[c] for shards in plan for c, a, b in shards)
+        load = [sum(b - a for _, a, b in shards) for shards in plan]
+        assert max(load) - min(load) <= max(clip_frames)
+    assert plan == SH.plan_clip_shards(clip_frames, world)         # deterministic: every rank derives the same plan
+
+
+def test_multi_clip_partials_equal_per_clip_single_pass(vqa):
+    """Any rank count gives the same per-clip means as one pass per clip (<= 1e-12), integers identical."""
+    from rtvqa_b200 import _native as N
+    from rtvqa_b200 import sharding as SH
+    rng = np.random.default_rng(5)
+    lens = [17, 4, 9]
+    tables = []
+    for k in lens:
+        t = np.zeros(k, dtype=N.FRAME_DTYPE)
+        for name in SH.SERIES:
+            t[name] = rng.integers(0, 1000, k) if name in ("edge_count", "orb_count") else rng.normal(size=k) * 10
+        tables.append(t)
+
+    def rows_of(clip, a, b):
+        return tables[clip][a:b]
+
+    want_p, want_i = SH.multi_clip_partials(SH.plan_clip_shards(lens, 1)[0], rows_of, lens, 0.8, _host_partial)
+    for world in (2, 3, 8):
+        plan = SH.plan_clip_shards(lens, world)
+        parts = [SH.multi_clip_partials(plan[r], rows_of, lens, 0.8, _host_partial) for r in range(world)]
+        got_p, got_i = sum(p for p, _ in parts), sum(i for _, i in parts)
+        np.testing.assert_allclose(got_p, want_p, rtol=1e-12)
+        assert np.array_equal(got_i, want_i)
+    for c, k in enumerate(lens):                                   # and it is the reference's smoothed mean
+        for si, name in enumerate(SH.SERIES):
+            x = np.asarray(tables[c][name][SH.FIRST[name]:], dtype=np.float64)
+            assert want_p[c, si] == pytest.approx(NO.smoothed_mean(x, 0.8), rel=1e-12)
