@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define VQA_ABI_VERSION 1
+#define VQA_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define VQA_API __attribute__((visibility("default")))
@@ -59,7 +59,28 @@ typedef struct vqa_cfg {
     int32_t resize_height;    /* config.json resize_height (video_processing.py:187) */
     uint32_t metrics_mask;    /* VQA_M_* */
     int32_t dct_impl;         /* 0 = auto (tcgen05 tensor-core contraction), 1 = force fp32 SIMT check kernel */
+    int32_t orb_width;        /* ORB input size: 0 = the reference's hard-wired 64x64 (complexity_metrics.py:386); */
+    int32_t orb_height;       /* otherwise gray(resize(frame, (orb_width, orb_height))) through the full ORB pipeline */
 } vqa_cfg;
+
+/* cv2.ORB_create(nfeatures, scaleFactor, nlevels, edgeThreshold, ..., fastThreshold) parameters
+ * (complexity_metrics.py:385 uses the defaults: 500, 1.2, 8, 31, 20; HARRIS score, patch 31) */
+typedef struct vqa_orb_cfg {
+    int32_t nfeatures;
+    int32_t nlevels;          /* 1..16 */
+    int32_t edge_threshold;   /* >= 4 */
+    int32_t fast_threshold;
+    float scale_factor;       /* > 1 */
+} vqa_orb_cfg;
+
+/* One detected keypoint (cv2.KeyPoint fields that exist before orientation / descriptors). */
+typedef struct vqa_keypoint {
+    float x, y;               /* level-0 coordinates: level coordinates * scale_factor^octave */
+    float response;           /* Harris response (orb.cpp HarrisResponses), bit-exact */
+    int32_t octave;           /* pyramid level */
+    int32_t lx, ly;           /* integer coordinates inside the level image */
+    int32_t fast_score;       /* FAST-9/16 corner score (strength - 1) */
+} vqa_keypoint;
 
 /* One row per analysed frame.  Field <- reference return value. */
 typedef struct vqa_frame_metrics {
@@ -115,6 +136,18 @@ VQA_API int vqa_kernel_report(vqa_ctx *ctx, char *buf, size_t cap);
 VQA_API int vqa_complexity_frames(vqa_ctx *ctx, const uint8_t *bgr, int n, int h, int w, size_t frame_stride,
                           const uint8_t *halo, int on_device, const vqa_cfg *cfg, vqa_frame_metrics *out);
 
+/* ---- a8 at any size: ORB keypoint detection and scoring -------------------
+ * cv2.ORB_create(...).detectAndCompute(gray, None) up to the keypoint list, on n one-channel frames
+ * (rows of w bytes, frames `frame_stride` bytes apart).  counts[i] = len(keypoints) of frame i;
+ * level_counts (optional) is [n][16]; kps (optional) receives up to kp_cap keypoints per frame,
+ * grouped by octave, unordered inside an octave.  cfg NULL = ORB_create() defaults.
+ * vqa_orb_describe is host-only (no context): pyramid level sizes and per-level feature quotas;
+ * returns the number of levels. */
+VQA_API void vqa_orb_default_cfg(vqa_orb_cfg *cfg);
+VQA_API int vqa_orb_describe(const vqa_orb_cfg *cfg, int h, int w, int32_t *level_w, int32_t *level_h, int32_t *quota);
+VQA_API int vqa_orb_detect(vqa_ctx *ctx, const uint8_t *gray, int n, int h, int w, size_t frame_stride, int on_device,
+                           const vqa_orb_cfg *cfg, int32_t *counts, int32_t *level_counts, vqa_keypoint *kps, int kp_cap);
+
 /* ---- a13: PSNR + SSIM of yuv420p (or any 3-plane 8-bit) frame pairs -------------------------
  * Replaces the psnr= and ssim= filter graphs run_ffmpeg_metrics builds
  * (video_processing.py:270-297); `main` is the distorted input [0:v], `ref` the reference
@@ -155,6 +188,11 @@ VQA_API int vqa_debug_hist(vqa_ctx *ctx, const uint8_t *bgr, int h, int w, int r
 VQA_API int vqa_debug_orb(vqa_ctx *ctx, const uint8_t *bgr, int h, int w, int32_t *out117);
 VQA_API int vqa_debug_canny(vqa_ctx *ctx, const uint8_t *gray, int h, int w, uint8_t *edges_out /* 0/255 */);
 VQA_API int vqa_debug_flow(vqa_ctx *ctx, const uint8_t *prev_gray, const uint8_t *next_gray, int h, int w, float *flow_out /* h*w*2 */);
+/* level `level` (>= 1) of the ORB pyramid of one gray frame (INTER_LINEAR_EXACT chain), dense rows */
+VQA_API int vqa_debug_orb_pyramid(vqa_ctx *ctx, const uint8_t *gray, int h, int w, const vqa_orb_cfg *cfg, int level,
+                                  uint8_t *level_out);
+/* host-only: packed (offset << 16 | weight of the right tap, 8.8 fixed point) taps of INTER_LINEAR_EXACT */
+VQA_API int vqa_debug_exact_taps(int src_len, int dst_len, uint32_t *taps_out);
 VQA_API int vqa_debug_dct(vqa_ctx *ctx, const uint8_t *gray, int h, int w, int impl, float *coef_out /* h*w */);
 
 #ifdef __cplusplus

@@ -134,5 +134,57 @@ def main():
     print("wrote", GOLD)
 
 
+def orb_general(gray, **kw):
+    """Keypoints of cv2.ORB_create(**kw).detectAndCompute(gray, None) -- the call the reference makes at
+    complexity_metrics.py:385-387, at sizes other than its hard-wired 64x64 -- as per-level counts and
+    a digest of the sorted (octave, response) list."""
+    import cv2
+    orb = cv2.ORB_create(**kw)
+    kps, _ = orb.detectAndCompute(gray, None)
+    nl = kw.get("nlevels", 8)
+    per = [sum(1 for k in kps if k.octave == l) for l in range(nl)]
+    rr = np.array(sorted((k.octave, float(np.float32(k.response))) for k in kps), dtype=np.float64).reshape(-1, 2)
+    key = np.concatenate([rr[:, 0].astype(np.int32).view(np.uint8), rr[:, 1].astype(np.float32).view(np.uint8)])
+    return dict(count=len(kps), per_level=per, digest=sha(key))
+
+
+ORB_CONFIGS = {
+    "default": {},
+    "n1000": dict(nfeatures=1000),
+    "n200_l4_s15": dict(nfeatures=200, nlevels=4, scaleFactor=1.5),
+    "edge16_fast10": dict(edgeThreshold=16, fastThreshold=10),
+}
+
+
+def main_orb():
+    """tests/golden/orb_general.json: cv2's ORB on the synthetic frames."""
+    import cv2
+    S = _load_synth()
+    g = dict(meta=dict(cv2=cv2.__version__, source="cv2.ORB_create(**cfg).detectAndCompute(gray, None)"), cases=[])
+    small = np.load(os.path.join(GOLD, "small_clip.npz"))["clip"]
+    mid = S.synth_clip(5, 270, 480, seed=3)
+    hd = S.synth_clip(3, 1080, 1920, seed=0)
+    rng = np.random.default_rng(21)
+    noise = rng.integers(0, 256, (200, 333), dtype=np.uint8)
+    frames = [("small", i, cv2.cvtColor(small[i], cv2.COLOR_BGR2GRAY)) for i in (0, 5, 11)]
+    frames += [("mid", i, cv2.cvtColor(mid[i], cv2.COLOR_BGR2GRAY)) for i in (0, 4)]
+    frames += [("hd", 1, cv2.cvtColor(hd[1], cv2.COLOR_BGR2GRAY))]
+    frames += [("noise_200x333_seed21", 0, noise)]
+    # resize -> gray order of the orb_size knob: gray(resize(frame, (w, h))), INTER_LINEAR
+    frames += [("hd_resized_640x360", 1, cv2.cvtColor(cv2.resize(hd[1], (640, 360)), cv2.COLOR_BGR2GRAY))]
+    for name, idx, gray in frames:
+        for cname, cfg in ORB_CONFIGS.items():
+            if name == "hd" and cname not in ("default", "n1000"):
+                continue
+            g["cases"].append(dict(clip=name, frame=idx, shape=list(gray.shape), gray_sha=sha(gray), cfg=cname,
+                                   **orb_general(gray, **cfg)))
+    with open(os.path.join(GOLD, "orb_general.json"), "w") as f:
+        json.dump(g, f, indent=1)
+    print("wrote orb_general.json:", len(g["cases"]), "cases")
+
+
 if __name__ == "__main__":
-    main()
+    if "--orb" in sys.argv:
+        main_orb()
+    else:
+        main()

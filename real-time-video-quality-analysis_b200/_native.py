@@ -23,7 +23,9 @@ EXPORTS = [
     "vqa_kernel_launches", "vqa_stage_ms", "vqa_reset_timers", "vqa_complexity_frames",
     "vqa_psnr_ssim_planar", "vqa_analyze_clip", "vqa_framerate_series", "vqa_ewm_partial", "vqa_debug_gray",
     "vqa_debug_resize", "vqa_debug_hist", "vqa_debug_orb", "vqa_kernel_profile", "vqa_kernel_report", "vqa_debug_canny", "vqa_debug_flow", "vqa_debug_dct",
+    "vqa_orb_default_cfg", "vqa_orb_describe", "vqa_orb_detect", "vqa_debug_orb_pyramid", "vqa_debug_exact_taps",
 ]
+ABI_VERSION = 2
 
 
 class VqaError(RuntimeError):
@@ -32,7 +34,23 @@ class VqaError(RuntimeError):
 
 class Cfg(C.Structure):
     _fields_ = [("resize_width", C.c_int32), ("resize_height", C.c_int32),
-                ("metrics_mask", C.c_uint32), ("dct_impl", C.c_int32)]
+                ("metrics_mask", C.c_uint32), ("dct_impl", C.c_int32),
+                ("orb_width", C.c_int32), ("orb_height", C.c_int32)]
+
+
+class OrbCfg(C.Structure):
+    """cv2.ORB_create(nfeatures, scaleFactor, nlevels, edgeThreshold, fastThreshold=...) (vqa_orb_cfg)."""
+    _fields_ = [("nfeatures", C.c_int32), ("nlevels", C.c_int32), ("edge_threshold", C.c_int32),
+                ("fast_threshold", C.c_int32), ("scale_factor", C.c_float)]
+
+
+def orb_cfg(nfeatures=500, scale_factor=1.2, nlevels=8, edge_threshold=31, fast_threshold=20) -> OrbCfg:
+    return OrbCfg(int(nfeatures), int(nlevels), int(edge_threshold), int(fast_threshold), float(scale_factor))
+
+
+KEYPOINT_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("response", "<f4"), ("octave", "<i4"), ("lx", "<i4"),
+                           ("ly", "<i4"), ("fast_score", "<i4")], align=True)
+ORB_MAX_LEVELS = 16
 
 
 FRAME_DTYPE = np.dtype([("hist_entropy", "<f4"), ("color_entropy", "<f4"), ("dct_energy", "<f4"),
@@ -86,7 +104,14 @@ def load_library():
         L.vqa_kernel_report.argtypes = [vp, C.c_char_p, C.c_size_t]
         L.vqa_debug_flow.argtypes = [vp, u8p, u8p, C.c_int, C.c_int, vp]
         L.vqa_debug_dct.argtypes = [vp, u8p, C.c_int, C.c_int, C.c_int, vp]
-        if L.vqa_abi_version() != 1:
+        L.vqa_orb_default_cfg.argtypes = [C.POINTER(OrbCfg)]
+        L.vqa_orb_default_cfg.restype = None
+        L.vqa_orb_describe.argtypes = [C.POINTER(OrbCfg), C.c_int, C.c_int, i32p, i32p, i32p]
+        L.vqa_orb_detect.argtypes = [vp, u8p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_int, C.POINTER(OrbCfg),
+                                     vp, vp, vp, C.c_int]
+        L.vqa_debug_orb_pyramid.argtypes = [vp, u8p, C.c_int, C.c_int, C.POINTER(OrbCfg), C.c_int, u8p]
+        L.vqa_debug_exact_taps.argtypes = [C.c_int, C.c_int, vp]
+        if L.vqa_abi_version() != ABI_VERSION:
             raise VqaError("libvqa_b200.so ABI version mismatch")
         _lib = L
         return L
@@ -161,9 +186,10 @@ class Context:
         self._check(self.lib.vqa_sync(self.h), "vqa_sync")
 
     # ------------------------------------------------------------------ a1-a8
-    def complexity_frames(self, frames, resize_width, resize_height, mask=M_ALL, halo=None, dct_impl=0):
+    def complexity_frames(self, frames, resize_width, resize_height, mask=M_ALL, halo=None, dct_impl=0, orb_size=None):
         """frames: (n,h,w,3) uint8 BGR -- numpy (host) or CUDA torch tensor.  Returns a structured
-        array (FRAME_DTYPE) with one row per frame."""
+        array (FRAME_DTYPE) with one row per frame.  ``orb_size`` = (width, height) runs the full ORB
+        pipeline on gray(resize(frame, orb_size)); None keeps the reference's hard-wired 64x64."""
         if _is_torch_tensor(frames):
             if not frames.is_cuda:
                 frames = frames.numpy()
@@ -196,13 +222,60 @@ class Context:
                 hptr = halo.ctypes.data
             keep = (frames, halo)
         out = np.zeros(n, dtype=FRAME_DTYPE)
-        cfg = Cfg(int(resize_width), int(resize_height), int(mask), int(dct_impl))
+        ow, oh = (int(orb_size[0]), int(orb_size[1])) if orb_size else (0, 0)
+        cfg = Cfg(int(resize_width), int(resize_height), int(mask), int(dct_impl), ow, oh)
         with self.lock:
             rc = self.lib.vqa_complexity_frames(self.h, C.c_void_p(ptr), n, h, w, stride,
                                                 C.c_void_p(hptr) if hptr else None, on_dev, C.byref(cfg),
                                                 C.c_void_p(out.ctypes.data))
         self._check(rc, "vqa_complexity_frames")
         del keep
+        return out
+
+    # ------------------------------------------------------------------ a8 at any size
+    def orb_detect(self, gray, cfg: OrbCfg | None = None, keypoints: bool = False, kp_cap: int = 4096):
+        """cv2.ORB_create(...).detectAndCompute(gray, None) up to the keypoint list.  gray: (h,w) or
+        (n,h,w) uint8, numpy or CUDA tensor.  Returns (counts[n], level_counts[n,16]) and, with
+        ``keypoints``, a list of KEYPOINT_DTYPE arrays (grouped by octave, unordered inside one)."""
+        on_dev = int(_is_torch_tensor(gray) and gray.is_cuda)
+        if on_dev:
+            import torch
+            g = gray.contiguous()
+            if g.dim() == 2:
+                g = g[None]
+            if g.dtype != torch.uint8 or g.dim() != 3:
+                raise TypeError("expected (n,h,w) uint8 gray frames")
+            torch.cuda.current_stream(g.device).synchronize()
+            ptr = g.data_ptr()
+        else:
+            g = _np_u8(gray)
+            if g.ndim == 2:
+                g = g[None]
+            if g.ndim != 3:
+                raise TypeError("expected (n,h,w) uint8 gray frames")
+            ptr = g.ctypes.data
+        n, h, w = (int(v) for v in g.shape)
+        counts = np.zeros(n, np.int32)
+        levels = np.zeros((n, ORB_MAX_LEVELS), np.int32)
+        kps = np.zeros((n, kp_cap), KEYPOINT_DTYPE) if keypoints else None
+        with self.lock:
+            rc = self.lib.vqa_orb_detect(self.h, C.c_void_p(ptr), n, h, w, h * w, on_dev,
+                                         C.byref(cfg) if cfg is not None else None, C.c_void_p(counts.ctypes.data),
+                                         C.c_void_p(levels.ctypes.data),
+                                         C.c_void_p(kps.ctypes.data) if keypoints else None, kp_cap if keypoints else 0)
+        self._check(rc, "vqa_orb_detect")
+        del g
+        if keypoints:
+            return counts, levels, [kps[i, :min(int(counts[i]), kp_cap)] for i in range(n)]
+        return counts, levels
+
+    def debug_orb_pyramid(self, gray, level, cfg: OrbCfg | None = None):
+        g = _np_u8(gray)
+        lw, lh, _ = orb_describe(g.shape[0], g.shape[1], cfg)
+        out = np.empty((lh[level], lw[level]), np.uint8)
+        self._check(self.lib.vqa_debug_orb_pyramid(self.h, g.ctypes.data, g.shape[0], g.shape[1],
+                                                   C.byref(cfg) if cfg is not None else None, level, out.ctypes.data),
+                    "vqa_debug_orb_pyramid")
         return out
 
     # ------------------------------------------------------------------ a13
@@ -240,7 +313,8 @@ class Context:
         del keep
         return out
 
-    def analyze_clip(self, frames, resize_width, resize_height, main_planes, ref_planes, mask=M_ALL, dct_impl=0):
+    def analyze_clip(self, frames, resize_width, resize_height, main_planes, ref_planes, mask=M_ALL, dct_impl=0,
+                     orb_size=None):
         """Host-buffer fast path for one clip: complexity rows + PSNR/SSIM rows with one interleaved
         upload schedule (vqa_analyze_clip).  frames (n,h,w,3) uint8; planes 3 x [n_pairs,h_c,w_c] uint8."""
         frames = _np_u8(frames)
@@ -261,7 +335,8 @@ class Context:
             keep += [a, b]
         rows = np.zeros(n, dtype=FRAME_DTYPE)
         fr = np.zeros(npairs, dtype=FR_DTYPE)
-        cfg = Cfg(int(resize_width), int(resize_height), int(mask), int(dct_impl))
+        ow, oh = (int(orb_size[0]), int(orb_size[1])) if orb_size else (0, 0)
+        cfg = Cfg(int(resize_width), int(resize_height), int(mask), int(dct_impl), ow, oh)
         with self.lock:
             rc = self.lib.vqa_analyze_clip(self.h, C.c_void_p(frames.ctypes.data), n, h, w, h * w * 3, C.byref(cfg),
                                            C.c_void_p(rows.ctypes.data), mp, rp, pw, ph, st, npairs,
@@ -346,6 +421,26 @@ class Context:
         out = np.empty(g.shape, np.float32)
         self._check(self.lib.vqa_debug_dct(self.h, g.ctypes.data, g.shape[0], g.shape[1], impl, out.ctypes.data), "debug_dct")
         return out
+
+
+def orb_describe(h: int, w: int, cfg: OrbCfg | None = None):
+    """Host-only (no GPU): ORB pyramid level widths, heights and per-level feature quotas."""
+    L = load_library()
+    lw, lh, q = ((C.c_int32 * ORB_MAX_LEVELS)() for _ in range(3))
+    n = L.vqa_orb_describe(C.byref(cfg) if cfg is not None else None, int(h), int(w), lw, lh, q)
+    if n < 0:
+        raise VqaError(f"vqa_orb_describe failed ({n})")
+    return list(lw[:n]), list(lh[:n]), list(q[:n])
+
+
+def exact_taps(src_len: int, dst_len: int):
+    """Host-only: INTER_LINEAR_EXACT taps of the ORB pyramid as (offset, weight_right) arrays (8.8 fixed point)."""
+    L = load_library()
+    out = np.zeros(int(dst_len), np.uint32)
+    rc = L.vqa_debug_exact_taps(int(src_len), int(dst_len), C.c_void_p(out.ctypes.data))
+    if rc != 0:
+        raise VqaError(f"vqa_debug_exact_taps failed ({rc})")
+    return (out >> 16).astype(np.int64), (out & 0xFFFF).astype(np.int64)
 
 
 _contexts: dict = {}

@@ -32,6 +32,25 @@ logger = logging.getLogger(__name__)
 
 use_gpu = True  # kept for source compatibility; the B200 path is the only path
 
+# ORB input size (width, height).  None = the reference's hard-wired 64x64 (:386), where ORB degenerates
+# to a {0, 1} count; a size runs the full pipeline (8-level pyramid, FAST, Harris, retainBest) on
+# gray(resize(frame, size)) -- SURVEY.md 8 f2.  Per-call ``orb_size=`` arguments override it.
+ORB_SIZE = None
+
+
+def set_orb_size(size):
+    """Module-wide ``orb_size`` knob: (width, height), or None for the reference's 64x64."""
+    global ORB_SIZE
+    if size is not None:
+        size = (int(size[0]), int(size[1]))
+        if size[0] <= 0 or size[1] <= 0:
+            raise ValueError("orb_size must be positive (width, height)")
+    ORB_SIZE = size
+
+
+def _orb_size(orb_size):
+    return ORB_SIZE if orb_size is None else (int(orb_size[0]), int(orb_size[1]))
+
 
 # --------------------------------------------------------------------------- frame source
 def validate_video_path(input_path):
@@ -128,8 +147,8 @@ def process_frame_interval_for_parallel(timestamps):
 
 
 # --------------------------------------------------------------------------- per-item operators
-def _one(frame, rw, rh, mask):
-    return N.get_context().complexity_frames(np.asarray(frame)[None], rw, rh, mask)[0]
+def _one(frame, rw, rh, mask, orb_size=None):
+    return N.get_context().complexity_frames(np.asarray(frame)[None], rw, rh, mask, orb_size=orb_size)[0]
 
 
 def process_frame_complexity(frame_pair):
@@ -148,9 +167,10 @@ def process_dct_frame(frame, resize_width, resize_height):
     return np.float32(_one(frame, resize_width, resize_height, N.M_DCT)["dct_energy"])
 
 
-def process_orb_frame_for_parallel(frame):
-    """ORB keypoint count on the 64x64 gray resize (reference :367-389).  int."""
-    return int(_one(frame, 64, 64, N.M_ORB)["orb_count"])
+def process_orb_frame_for_parallel(frame, orb_size=None):
+    """ORB keypoint count on the 64x64 gray resize (reference :367-389).  int.  ``orb_size`` (or the
+    module knob ``ORB_SIZE``) replaces the hard-wired 64x64 by any (width, height)."""
+    return int(_one(frame, 64, 64, N.M_ORB, _orb_size(orb_size))["orb_count"])
 
 
 def process_histogram_frame(frame, resize_width, resize_height):
@@ -250,21 +270,22 @@ def process_in_batches(frames, process_func, num_workers, batch_size=100, **kwar
         for i in range(0, len(frames), batch_size):
             batch = frames[i:i + batch_size]
             shapes = {np.asarray(f).shape for f in batch}
+            osz = _orb_size(kw.get("orb_size")) if name == "process_orb_frame_for_parallel" else None
             if len(shapes) == 1:
-                r = ctx.complexity_frames(np.stack([np.asarray(f) for f in batch]), rw, rh, mask)
+                r = ctx.complexity_frames(np.stack([np.asarray(f) for f in batch]), rw, rh, mask, orb_size=osz)
                 results.extend(cast(v) for v in r[field])
             else:  # ragged batch: one call per frame
                 for f in batch:
-                    results.append(cast(ctx.complexity_frames(np.asarray(f)[None], rw, rh, mask)[field][0]))
+                    results.append(cast(ctx.complexity_frames(np.asarray(f)[None], rw, rh, mask, orb_size=osz)[field][0]))
         return results
     raise AssertionError("unreachable")
 
 
 # --------------------------------------------------------------------------- clip level
-def _clip_metrics(frames, resize_width, resize_height, batch_size=100, halo=None, mask=N.M_ALL):
+def _clip_metrics(frames, resize_width, resize_height, batch_size=100, halo=None, mask=N.M_ALL, orb_size=None):
     """All per-frame and pair metrics of consecutive sampled frames in one device pass."""
     ctx = N.get_context()
-    return ctx.complexity_frames(frames, resize_width, resize_height, mask, halo=halo)
+    return ctx.complexity_frames(frames, resize_width, resize_height, mask, halo=halo, orb_size=_orb_size(orb_size))
 
 
 def _stack_sampled(frame_pairs):
@@ -290,7 +311,8 @@ def calculate_temporal_dct(video_path, resize_width, resize_height, frame_interv
 STREAM_CHUNK_FRAMES = 48      # sampled frames per decode chunk (= the device chunk of vqa_complexity_frames)
 
 
-def stream_clip_metrics(video_path, resize_width, resize_height, frame_interval=10, chunk_frames=None, mask=N.M_ALL):
+def stream_clip_metrics(video_path, resize_width, resize_height, frame_interval=10, chunk_frames=None, mask=N.M_ALL,
+                        orb_size=None):
     """Single-decode streaming analysis of a clip.  Decodes in a background thread,
     pushes chunks of sampled frames through the device with the previous chunk's last frame as
     halo, and returns ``(rows, timestamps)``: one FRAME_DTYPE row per sampled frame ``s_0 .. s_{K-1}``
@@ -302,21 +324,24 @@ def stream_clip_metrics(video_path, resize_width, resize_height, frame_interval=
     for chunk in src:
         if ctx is None:
             ctx = N.get_context()
-        parts.append(ctx.complexity_frames(chunk, resize_width, resize_height, mask, halo=halo))
+        parts.append(ctx.complexity_frames(chunk, resize_width, resize_height, mask, halo=halo,
+                                           orb_size=_orb_size(orb_size)))
         halo = chunk[-1]
     rows = np.concatenate(parts) if parts else None
     return rows, list(src.timestamps)
 
 
 def calculate_average_scene_complexity(video_path, resize_width, resize_height, frame_interval=10,
-                                       smoothing_factor=0.8, num_workers=None, batch_size=100):
+                                       smoothing_factor=0.8, num_workers=None, batch_size=100, *, orb_size=None):
     """Reference :246-310.  Returns, in the reference's order, the means of the EWM-smoothed
     series of: motion, dct, histogram, edge, orb, colour histogram, temporal dct, framerate.
-    One decode of the file (the reference makes three) feeds every metric and the timestamps."""
+    One decode of the file (the reference makes three) feeds every metric and the timestamps.
+    ``orb_size`` (keyword-only extension, default = module knob ``ORB_SIZE`` = the reference's 64x64)."""
     if num_workers is None:
         num_workers = multiprocessing.cpu_count() // 2      # accepted for API compatibility
     a = smoothing_factor
-    r, frame_timestamps = stream_clip_metrics(video_path, resize_width, resize_height, frame_interval)
+    r, frame_timestamps = stream_clip_metrics(video_path, resize_width, resize_height, frame_interval,
+                                              orb_size=orb_size)
     if r is None or len(r) < 2:                              # fewer than one (current, previous) pair
         nan = np.float64("nan")
         motion = dct = hist = edge = orb = color = nan

@@ -162,6 +162,7 @@ void vqa_destroy(vqa_ctx *c)
     cudaStreamSynchronize(c->copy_stream);
     cudaStreamSynchronize(c->side_stream);
     dct_umma_release(c);
+    orb_release(c);
     for (auto &kv : c->bufs) if (kv.second.p) cudaFree(kv.second.p);
     for (auto &kv : c->pinned) if (kv.second.p) cudaFreeHost(kv.second.p);
     for (auto &kv : c->timers) for (auto &p : kv.second.ev) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
@@ -258,7 +259,7 @@ int vqa_stage_ms(vqa_ctx *c, const char *stage, double *ms, uint64_t *launches)
 }
 
 // ------------------------------------------------------------------------------------------
-static int pick_chunk(vqa_ctx *c, int h, int w, int rw, int rh, unsigned mask)
+static int pick_chunk(vqa_ctx *c, int h, int w, int rw, int rh, unsigned mask, int ow = 0, int oh = 0)
 {
     const char *env = getenv("VQA_CHUNK");
     if (env && atoi(env) > 0) return atoi(env);
@@ -267,6 +268,7 @@ static int pick_chunk(vqa_ctx *c, int h, int w, int rw, int rh, unsigned mask)
     double per = hw * 3 * 3 + hw * 2 + rr * 8;                         // input double buffer, gray, labels/state
     if (mask & VQA_M_MOTION) per += hw * 66;                           // I, R, M, 2 x flow
     if (mask & (VQA_M_DCT | VQA_M_TDCT)) per += rr * 16;               // X, T (hi/lo), C
+    if ((mask & VQA_M_ORB) && ow > 0 && !(ow == 64 && oh == 64)) per += (double)ow * oh * 17;   // bgr+gray, pyramid, 3 lists
     // scratch already held by this context is reusable, so count it as free
     size_t held = 0;
     for (auto &kv : c->bufs) held += kv.second.cap;
@@ -344,8 +346,14 @@ int complexity_body(vqa_ctx *c, const uint8_t *bgr, int n, int h, int w, size_t 
     const bool want_hist = mask & (VQA_M_HIST | VQA_M_COLOR), want_edge = mask & VQA_M_EDGE;
     const bool want_dct = mask & (VQA_M_DCT | VQA_M_TDCT), want_tdct = mask & VQA_M_TDCT;
     const bool want_motion = mask & VQA_M_MOTION, want_orb = mask & VQA_M_ORB;
-    const bool need_full_gray = want_motion || want_dct || (identity && (want_hist || want_edge));
-    const int CH = std::min(n, pick_chunk(c, h, w, rw, rh, mask));
+    // ORB input: the reference's 64x64 (four live pixels, fast_orb.cu) unless the orb_size knob asks for the
+    // full pipeline on gray(resize(frame, (ow, oh)))
+    const int ow = cfg->orb_width, oh = cfg->orb_height;
+    if ((ow > 0) != (oh > 0) || ow < 0 || oh < 0) return set_err(c, VQA_E_INVALID, "orb_width / orb_height must both be set or both 0");
+    const bool orb_general = want_orb && ow > 0 && !(ow == 64 && oh == 64);
+    const bool orb_native = orb_general && ow == w && oh == h;
+    const bool need_full_gray = want_motion || want_dct || (identity && (want_hist || want_edge)) || orb_native;
+    const int CH = std::min(n, pick_chunk(c, h, w, rw, rh, mask, cfg->orb_width, cfg->orb_height));
 
     // per-clip result arrays on the device
     VQA_BUF(c, d_hent, float, "res.hent", n);
@@ -362,6 +370,12 @@ int complexity_body(vqa_ctx *c, const uint8_t *bgr, int n, int h, int w, size_t 
     if (!identity) {
         if (want_hist || want_edge) { VQA_BUF(c, gs_, uint8_t, "ing.gray_small", RR * CH); gs = gs_; }
         if (want_dct) { VQA_BUF(c, xs_, uint8_t, "ing.dct_in", RR * (CH + 1)); xs = xs_; }
+    }
+    uint8_t *orb_bgr = nullptr, *orb_gray = nullptr;
+    if (orb_general && !orb_native) {
+        VQA_BUF(c, ob_, uint8_t, "orb.in_bgr", (size_t)ow * oh * 3 * CH);
+        VQA_BUF(c, og_, uint8_t, "orb.in_gray", (size_t)ow * oh * CH);
+        orb_bgr = ob_; orb_gray = og_;
     }
     float *Cbuf = nullptr;
     if (want_dct) { VQA_BUF(c, cb_, float, "dct.coef", RR * (CH + 1)); Cbuf = cb_; }
@@ -480,7 +494,16 @@ int complexity_body(vqa_ctx *c, const uint8_t *bgr, int n, int h, int w, size_t 
             }
             if (want_orb) {
                 stage_begin(c, "orb");
-                if ((rc = run_orb64(c, src, m, h, w, stride, d_orb + s))) return rc;
+                if (!orb_general) {
+                    if ((rc = run_orb64(c, src, m, h, w, stride, d_orb + s))) return rc;
+                } else if (orb_native) {
+                    if ((rc = run_orb_general(c, Gc, m, h, w, HW, w, nullptr, d_orb + s, nullptr, nullptr, 0))) return rc;
+                } else {
+                    const size_t OW = (size_t)ow * oh;
+                    if ((rc = run_resize_u8(c, src, m, h, w, 3, stride, ow, oh, orb_bgr))) return rc;
+                    if ((rc = run_gray_hist(c, orb_bgr, m, oh, ow, OW * 3, orb_gray, nullptr))) return rc;
+                    if ((rc = run_orb_general(c, orb_gray, m, oh, ow, OW, ow, nullptr, d_orb + s, nullptr, nullptr, 0))) return rc;
+                }
                 stage_end(c, "orb");
             }
             if (want_dct) {
@@ -702,6 +725,70 @@ int vqa_psnr_ssim_planar(vqa_ctx *c, const uint8_t *const main_planes[3], const 
         }
         o.psnr_avg = o.mse_avg == 0 ? INFINITY : 10.0 * log10(255.0 * 255.0 / o.mse_avg);
     }
+    return VQA_OK;
+}
+
+// ------------------------------------------------------------------------------ general-size ORB
+void vqa_orb_default_cfg(vqa_orb_cfg *cfg) { if (cfg) orb_defaults(cfg); }
+
+int vqa_orb_describe(const vqa_orb_cfg *cfg, int h, int w, int32_t *level_w, int32_t *level_h, int32_t *quota)
+{
+    return orb_describe(cfg, h, w, level_w, level_h, quota);
+}
+
+int vqa_debug_exact_taps(int src_len, int dst_len, uint32_t *taps_out) { return orb_exact_taps(src_len, dst_len, taps_out); }
+
+int vqa_orb_detect(vqa_ctx *c, const uint8_t *gray, int n, int h, int w, size_t frame_stride, int on_device,
+                   const vqa_orb_cfg *cfg, int32_t *counts, int32_t *level_counts, vqa_keypoint *kps, int kp_cap)
+{
+    if (!c) return VQA_E_INVALID;
+    if (!gray || !counts || n < 0 || h <= 0 || w <= 0 || frame_stride < (size_t)h * w || (kps && kp_cap <= 0))
+        return set_err(c, VQA_E_INVALID, "vqa_orb_detect: bad argument");
+    if (n == 0) return VQA_OK;
+    VQA_CUDA(c, cudaSetDevice(c->device));
+    const size_t HW = (size_t)h * w;
+    const int CH = std::min(n, 16);
+    VQA_BUF(c, d_cnt, int, "orbd.cnt", CH);
+    VQA_BUF(c, d_lc, int, "orbd.lc", (size_t)CH * 16);
+    vqa_keypoint *d_kp = nullptr;
+    if (kps) { VQA_BUF(c, kp_, vqa_keypoint, "orbd.kp", (size_t)CH * kp_cap); d_kp = kp_; }
+    uint8_t *d_in = nullptr;
+    if (!on_device) { VQA_BUF(c, in_, uint8_t, "orbd.in", HW * CH); d_in = in_; }
+    stage_begin(c, "orb");
+    for (int s = 0; s < n; s += CH) {
+        const int m = std::min(CH, n - s);
+        const uint8_t *src = gray + (size_t)s * frame_stride;
+        size_t stride = frame_stride;
+        if (!on_device) {
+            VQA_CUDA(c, cudaMemcpy2DAsync(d_in, HW, src, frame_stride, HW, m, cudaMemcpyHostToDevice, c->stream));
+            src = d_in;
+            stride = HW;
+        }
+        int rc = run_orb_general(c, src, m, h, w, stride, w, cfg, d_cnt, d_lc, d_kp, kp_cap);
+        if (rc) return rc;
+        VQA_CUDA(c, cudaMemcpyAsync(counts + s, d_cnt, sizeof(int) * m, cudaMemcpyDeviceToHost, c->stream));
+        if (level_counts)
+            VQA_CUDA(c, cudaMemcpyAsync(level_counts + (size_t)s * 16, d_lc, sizeof(int) * 16 * m, cudaMemcpyDeviceToHost, c->stream));
+        if (kps)
+            VQA_CUDA(c, cudaMemcpyAsync(kps + (size_t)s * kp_cap, d_kp, sizeof(vqa_keypoint) * (size_t)kp_cap * m,
+                                        cudaMemcpyDeviceToHost, c->stream));
+        VQA_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    stage_end(c, "orb");
+    return VQA_OK;
+}
+
+int vqa_debug_orb_pyramid(vqa_ctx *c, const uint8_t *gray, int h, int w, const vqa_orb_cfg *cfg, int level, uint8_t *level_out)
+{
+    if (!c || !gray || !level_out || h <= 0 || w <= 0) return VQA_E_INVALID;
+    int32_t cnt = 0;
+    int rc = vqa_orb_detect(c, gray, 1, h, w, (size_t)h * w, 0, cfg, &cnt, nullptr, nullptr, 0);
+    if (rc) return rc;
+    const uint8_t *p = nullptr;
+    int pitch = 0, lh = 0, lw = 0;
+    if ((rc = orb_level_view(c, level, &p, &pitch, &lh, &lw))) return set_err(c, rc, "vqa_debug_orb_pyramid: no level %d", level);
+    VQA_CUDA(c, cudaMemcpy2DAsync(level_out, lw, p, pitch, lw, lh, cudaMemcpyDeviceToHost, c->stream));
+    VQA_CUDA(c, cudaStreamSynchronize(c->stream));
     return VQA_OK;
 }
 

@@ -59,6 +59,7 @@ struct vqa_ctx {
     uint64_t alloc_epoch = 1, free_epoch = 0;
     size_t free_cached = 0;
     void *umma = nullptr;                         // tensor-map cache of the tcgen05 DCT (dct_umma.cu)
+    void *orb = nullptr;                          // pyramid geometry cache of the general-size ORB (orb.cu)
 };
 
 namespace vqa {
@@ -187,6 +188,15 @@ int run_canny(vqa_ctx *c, const uint8_t *gray, int n, int h, int w, unsigned lon
 // fast_orb.cu
 int run_orb64(vqa_ctx *c, const uint8_t *bgr, int n, int h, int w, size_t frame_stride, int *counts /* [n] dev */,
               int *dbg = nullptr /* optional [116]: 10x10 window + 4x4 scores of frame 0 */);
+// orb.cu: general-size ORB (pyramid, FAST, Harris, retainBest); gray rows `pitch0` bytes apart
+void orb_defaults(vqa_orb_cfg *cfg);
+int run_orb_general(vqa_ctx *c, const uint8_t *gray, int n, int h, int w, size_t frame_stride, int pitch0,
+                    const vqa_orb_cfg *cfg, int *counts /* [n] dev */, int *level_counts /* [n][16] dev or null */,
+                    vqa_keypoint *kps /* [n][kp_cap] dev or null */, int kp_cap);
+int orb_describe(const vqa_orb_cfg *cfg, int h, int w, int32_t *level_w, int32_t *level_h, int32_t *quota);
+int orb_exact_taps(int sn, int dn, uint32_t *out);
+int orb_level_view(vqa_ctx *c, int level, const uint8_t **ptr, int *pitch, int *lh, int *lw);   // frame 0 of the last call
+void orb_release(vqa_ctx *c);
 // dct.cu / dct_umma.cu
 int run_dct(vqa_ctx *c, const uint8_t *x, int n, int h, int w, int impl, float *coef /* [n][h][w] dev */,
             double *energy /* [n] dev */);

@@ -84,6 +84,11 @@ def validate_config(config):
         raise ValueError("Frame interval must be a positive integer.")
     if not isinstance(config.get('num_workers', multiprocessing.cpu_count() // 2), int):
         raise ValueError("num_workers must be an integer.")
+    # optional extension: ORB input size; absent = the reference's hard-wired 64x64
+    ow, oh = config.get('orb_width'), config.get('orb_height')
+    if (ow is None) != (oh is None) or (ow is not None and (not isinstance(ow, int) or not isinstance(oh, int)
+                                                            or ow <= 0 or oh <= 0)):
+        raise ValueError("orb_width and orb_height must both be positive integers (or both absent).")
 
 
 def get_video_info(video_path):
@@ -141,13 +146,14 @@ def psnr_ssim_frames(main_planes, ref_planes, device=None):
     return N.get_context(device, role="fr").psnr_ssim(main_planes, ref_planes)
 
 
-def analyze_frames(frames, resize_width, resize_height, main_planes, ref_planes, device=None):
+def analyze_frames(frames, resize_width, resize_height, main_planes, ref_planes, device=None, orb_size=None):
     """Both halves of ``process_video_and_extract_metrics`` (reference :216 PSNR/SSIM, :242 scene
     complexity) for pre-decoded HOST buffers in one device pass with one interleaved upload schedule
     (``vqa_analyze_clip``): ``frames`` (n,h,w,3) uint8 BGR sampled frames, planes 3 x [n_pairs,h_c,w_c]
     uint8 (distorted = main, reference = ref).  Returns (complexity rows, PSNR/SSIM rows); identical to
     ``complexity_metrics._clip_metrics`` + ``psnr_ssim_frames`` called in turn."""
-    return N.get_context(device).analyze_clip(frames, resize_width, resize_height, main_planes, ref_planes)
+    return N.get_context(device).analyze_clip(frames, resize_width, resize_height, main_planes, ref_planes,
+                                              orb_size=orb_size)
 
 
 def _fmt_psnr(v):
@@ -245,8 +251,9 @@ def process_video_and_extract_metrics(input_video, config, correct_column_order=
                                             resolution=resolution, frame_rate=frame_rate)
         logger.info("Metrics extracted: %s", metrics)
         logger.info("Calculating scene complexity after encoding...")
+        orb_size = (config['orb_width'], config['orb_height']) if config.get('orb_width') else None
         vals = calculate_average_scene_complexity(encoded_video, resize_width, resize_height,
-                                                  frame_interval=frame_interval)
+                                                  frame_interval=frame_interval, orb_size=orb_size)
         metrics.update(complexity_columns(vals, correct_column_order))
         thread_safe_update_csv(metrics, csv_file='video_quality_data.csv')
     finally:

@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol(vqa):
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in vqa_b200.h but not exported"
     assert sorted(set(declared)) == sorted(set(N.EXPORTS)), "binding and header disagree on the entry points"
-    assert lib.vqa_abi_version() == 1
+    assert lib.vqa_abi_version() == N.ABI_VERSION == 2
 
 
 def test_struct_layouts_match_header(vqa, tmp_path):
@@ -51,16 +51,24 @@ int main(void) {
   printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(vqa_fr_metrics), offsetof(vqa_fr_metrics, sse), offsetof(vqa_fr_metrics, mse),
     offsetof(vqa_fr_metrics, mse_avg), offsetof(vqa_fr_metrics, psnr), offsetof(vqa_fr_metrics, psnr_avg),
     offsetof(vqa_fr_metrics, ssim), offsetof(vqa_fr_metrics, ssim_all));
-  printf("%zu\\n", sizeof(vqa_cfg));
+  printf("%zu %zu %zu\\n", sizeof(vqa_cfg), offsetof(vqa_cfg, orb_width), offsetof(vqa_cfg, orb_height));
+  printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(vqa_orb_cfg), offsetof(vqa_orb_cfg, nfeatures), offsetof(vqa_orb_cfg, nlevels),
+    offsetof(vqa_orb_cfg, edge_threshold), offsetof(vqa_orb_cfg, fast_threshold), offsetof(vqa_orb_cfg, scale_factor));
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(vqa_keypoint), offsetof(vqa_keypoint, x), offsetof(vqa_keypoint, y),
+    offsetof(vqa_keypoint, response), offsetof(vqa_keypoint, octave), offsetof(vqa_keypoint, lx), offsetof(vqa_keypoint, ly),
+    offsetof(vqa_keypoint, fast_score));
   return 0; }''')
     exe = tmp_path / "layout"
     subprocess.check_call(["gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
-    a, b, c = subprocess.check_output([str(exe)], text=True).strip().splitlines()
+    a, b, c, d, e = subprocess.check_output([str(exe)], text=True).strip().splitlines()
     f = N.FRAME_DTYPE
     assert [int(v) for v in a.split()] == [f.itemsize] + [f.fields[n][1] for n in f.names]
     g = N.FR_DTYPE
     assert [int(v) for v in b.split()] == [g.itemsize] + [g.fields[n][1] for n in g.names]
-    assert int(c) == ctypes.sizeof(N.Cfg)
+    assert [int(v) for v in c.split()] == [ctypes.sizeof(N.Cfg), N.Cfg.orb_width.offset, N.Cfg.orb_height.offset]
+    assert [int(v) for v in d.split()] == [ctypes.sizeof(N.OrbCfg)] + [getattr(N.OrbCfg, n).offset for n, _ in N.OrbCfg._fields_]
+    k = N.KEYPOINT_DTYPE
+    assert [int(v) for v in e.split()] == [k.itemsize] + [k.fields[n][1] for n in k.names]
 
 
 def test_product_package_never_imports_the_oracle():
