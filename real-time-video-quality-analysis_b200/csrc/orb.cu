@@ -161,57 +161,81 @@ __device__ __forceinline__ int fast_strength(const int v, const int (&p)[16])
     return best;
 }
 
-constexpr int FT = 32;                                   // FAST output tile (FT x FT), halo 1 (NMS) + 3 (ring)
-constexpr int FPW = FT + 8, FPP = FT + 12;               // pixel tile rows x padded pitch
-constexpr int FSW = FT + 2, FSP = FT + 4;                // score tile
+// FAST tile: FTW x FTH outputs per CTA; scores are needed one pixel further out (3x3 NMS) and pixels three
+// further still (ring radius) -> 4-pixel halo.  Three phases: (1) every score position takes the cheap
+// compass pre-test and the survivors are queued in shared memory, (2) the queue is processed densely (no
+// divergence between corner and non-corner lanes), (3) NMS + warp-aggregated append.
+constexpr int FTW = 64, FTH = 32;
+constexpr int PXH = FTH + 8, PXW = FTW + 8 + 4;          // pixel tile: 72 columns + <= 3 bytes of alignment slack
+constexpr int SCH = FTH + 2, SCW = FTW + 2, SCP = FTW + 4;
 
 __global__ void __launch_bounds__(256)
 k_orb_fast(const uint8_t *__restrict__ img, size_t frame_stride, int pitch, int lh, int lw, int edge, int thr,
            uint32_t *__restrict__ cand, size_t cand_frame, int *__restrict__ ncand, unsigned *__restrict__ shist,
            int ctr_stride)
 {
-    __shared__ uint8_t px[FPW][FPP];
-    __shared__ uint8_t sc[FSW][FSP];
-    const int frame = blockIdx.z, tid = threadIdx.y * 32 + threadIdx.x;
-    const int ox = edge + blockIdx.x * FT, oy = edge + blockIdx.y * FT;
+    __shared__ __align__(16) uint8_t px[PXH][PXW];
+    __shared__ uint8_t sc[SCH][SCP];
+    __shared__ unsigned short queue[SCH * SCW];
+    __shared__ int qn;
+    const int frame = blockIdx.z, tid = threadIdx.x;
+    const int ox = edge + blockIdx.x * FTW, oy = edge + blockIdx.y * FTH;
+    const int xa = (ox - 4) & ~3, sh = (ox - 4) - xa;      // tile columns start at a 4-byte boundary; ox - 4 >= 0
     const uint8_t *src = img + (size_t)frame * frame_stride;
-    for (int i = tid; i < FPW * FPW; i += 256) {
-        const int r = i / FPW, q = i - r * FPW;
-        const int gy = min(oy - 4 + r, lh - 1), gx = min(ox - 4 + q, lw - 1);   // ox, oy >= edge >= 4
-        px[r][q] = src[(size_t)gy * pitch + gx];
+    if (tid == 0) qn = 0;
+    if ((((size_t)src | (size_t)pitch) & 3) == 0) {         // 32-bit loads; words past the row end are clamped
+        const int maxw = (pitch >> 2) - 1;                  // (they only feed score positions that are skipped)
+        for (int i = tid; i < PXH * (PXW / 4); i += 256) {
+            const int r = i / (PXW / 4), q = i - r * (PXW / 4);
+            const int gy = min(oy - 4 + r, lh - 1), wi = min((xa >> 2) + q, maxw);
+            ((uint32_t *)px[r])[q] = ((const uint32_t *)(src + (size_t)gy * pitch))[wi];
+        }
+    } else {
+        for (int i = tid; i < PXH * PXW; i += 256) {
+            const int r = i / PXW, q = i - r * PXW;
+            const int gy = min(oy - 4 + r, lh - 1), gx = min(xa + q, lw - 1);
+            px[r][q] = src[(size_t)gy * pitch + gx];
+        }
     }
     __syncthreads();
-    // ring offsets of cv2's FAST-9/16, clockwise from (0, 3)
-    const int RX[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
-    const int RY[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
-    for (int i = tid; i < FSW * FSW; i += 256) {
-        const int r = i / FSW, q = i - r * FSW;            // score tile position; pixel tile position is +3
+    // (1) compass pre-test: a 9-arc of the 16-ring always holds two adjacent compass points
+    for (int i = tid; i < SCH * SCW; i += 256) {
+        const int r = i / SCW, q = i - r * SCW;            // score position (r, q) <-> pixel tile (r + 3, q + 3 + sh)
         const int gy = oy - 1 + r, gx = ox - 1 + q;
-        int s = 0;
         if (gy < lh - 3 && gx < lw - 3) {
-            const int v = px[r + 3][q + 3];
-            // necessary condition for a 9-arc: two adjacent compass points both beyond the threshold
-            const int d0 = v - px[r + 6][q + 3], d4 = v - px[r + 3][q + 6], d8 = v - px[r][q + 3], d12 = v - px[r + 3][q];
+            const int c = q + 3 + sh;
+            const int v = px[r + 3][c];
+            const int d0 = v - px[r + 6][c], d4 = v - px[r + 3][c + 3], d8 = v - px[r][c], d12 = v - px[r + 3][c - 3];
             const unsigned hi = (d0 > thr) | ((d4 > thr) << 1) | ((d8 > thr) << 2) | ((d12 > thr) << 3);
             const unsigned lo = (d0 < -thr) | ((d4 < -thr) << 1) | ((d8 < -thr) << 2) | ((d12 < -thr) << 3);
             const unsigned hh = hi & ((hi >> 1) | (hi << 3)), ll = lo & ((lo >> 1) | (lo << 3));
-            if ((hh | ll) & 0xfu) {
-                int p[16];
-#pragma unroll
-                for (int k = 0; k < 16; k++) p[k] = px[r + 3 + RY[k]][q + 3 + RX[k]];
-                const int st = fast_strength(v, p);
-                if (st > thr) s = st - 1;
-            }
+            if ((hh | ll) & 0xfu) queue[atomicAdd(&qn, 1)] = (unsigned short)i;
         }
-        sc[r][q] = (uint8_t)s;
+        sc[r][q] = 0;
     }
     __syncthreads();
+    // (2) full strength of the survivors; ring offsets of cv2's FAST-9/16, clockwise from (0, 3)
+    const int RX[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
+    const int RY[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
+    const int nq = qn;
+    for (int j = tid; j < nq; j += 256) {
+        const int i = queue[j], r = i / SCW, q = i - r * SCW, c = q + 3 + sh;
+        const int v = px[r + 3][c];
+        int p[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) p[k] = px[r + 3 + RY[k]][c + RX[k]];
+        const int st = fast_strength(v, p);
+        if (st > thr) sc[r][q] = (uint8_t)(st - 1);
+    }
+    __syncthreads();
+    // (3) 3x3 non-maximum suppression inside the border, append
     int *nc = ncand + (size_t)frame * ctr_stride;
     unsigned *hist = shist + (size_t)frame * ctr_stride * 256;
     uint32_t *list = cand + (size_t)frame * cand_frame;
+    const int lane = tid & 31, wrp = tid >> 5;
 #pragma unroll
-    for (int j = 0; j < FT / 8; j++) {
-        const int ty = threadIdx.y + 8 * j, tx = threadIdx.x;
+    for (int j = 0; j < (FTH / 8) * (FTW / 32); j++) {
+        const int ty = wrp * (FTH / 8) + j / (FTW / 32), tx = lane + 32 * (j % (FTW / 32));
         const int gy = oy + ty, gx = ox + tx;
         const int s = sc[ty + 1][tx + 1];
         bool ok = s > 0 && gy < lh - edge && gx < lw - edge;
@@ -225,7 +249,7 @@ k_orb_fast(const uint8_t *__restrict__ img, size_t frame_stride, int pitch, int 
         const unsigned m = __ballot_sync(0xffffffffu, ok);
         if (m) {
             int base = 0;
-            const int lane = threadIdx.x, leader = __ffs(m) - 1;
+            const int leader = __ffs(m) - 1;
             if (lane == leader) base = atomicAdd(nc, __popc(m));
             base = __shfl_sync(0xffffffffu, base, leader);
             if (ok) {
@@ -474,9 +498,9 @@ int run_orb_general(vqa_ctx *c, const uint8_t *gray, int n, int h, int w, size_t
     for (int l = 0; l < live; l++) {
         const uint8_t *img = l == 0 ? gray : pyr + L.pyr_off[l];
         const size_t iframe = l == 0 ? frame_stride : g->pyr_frame;
-        dim3 blk(32, 8), grd(cdiv(L.lw[l] - 2 * cfg.edge_threshold, FT), cdiv(L.lh[l] - 2 * cfg.edge_threshold, FT), n);
+        dim3 grd(cdiv(L.lw[l] - 2 * cfg.edge_threshold, FTW), cdiv(L.lh[l] - 2 * cfg.edge_threshold, FTH), n);
         VQA_BYTES(c, (double)n * L.lw[l] * L.lh[l]);
-        VQA_LAUNCH(c, k_orb_fast, grd, blk, 0, img, iframe, L.pitch[l], L.lh[l], L.lw[l], cfg.edge_threshold,
+        VQA_LAUNCH(c, k_orb_fast, grd, 256, 0, img, iframe, L.pitch[l], L.lh[l], L.lw[l], cfg.edge_threshold,
                    cfg.fast_threshold, cand + L.cand_off[l], g->cand_frame, ncand + l, shist + (size_t)l * 256, MAXL);
     }
     if (live > 0) {

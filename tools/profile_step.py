@@ -10,13 +10,14 @@ from rtvqa_b200 import _native as N
 F = int(sys.argv[1]) if len(sys.argv) > 1 else 24
 H = int(sys.argv[2]) if len(sys.argv) > 2 else 1080
 W = int(sys.argv[3]) if len(sys.argv) > 3 else 1920
+ORB = tuple(int(v) for v in os.environ["VQA_PROF_ORB"].lower().split("x")) if os.environ.get("VQA_PROF_ORB") else None
 ctx = N.Context(0)
 clip = torch.from_numpy(rtvqa_b200.synth.synth_clip(F, H, W, seed=0)).cuda()
 (ry, ru, rv), (dy, du, dv) = rtvqa_b200.synth.synth_yuv_pairs(4, H, W, seed=1)
-ctx.complexity_frames(clip, W, H)            # warm-up (allocations, tensor maps, basis)
+ctx.complexity_frames(clip, W, H, orb_size=ORB)            # warm-up (allocations, tensor maps, basis)
 torch.cuda.synchronize()
 torch.cuda.profiler.start()
-rows = ctx.complexity_frames(clip, W, H)
+rows = ctx.complexity_frames(clip, W, H, orb_size=ORB)
 fr = ctx.psnr_ssim((dy, du, dv), (ry, ru, rv))
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()
