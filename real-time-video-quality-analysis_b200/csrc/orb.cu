@@ -169,7 +169,7 @@ constexpr int FTW = 64, FTH = 32;
 constexpr int PXH = FTH + 8, PXW = FTW + 8 + 4;          // pixel tile: 72 columns + <= 3 bytes of alignment slack
 constexpr int SCH = FTH + 2, SCW = FTW + 2, SCP = FTW + 4;
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 5)
 k_orb_fast(const uint8_t *__restrict__ img, size_t frame_stride, int pitch, int lh, int lw, int edge, int thr,
            uint32_t *__restrict__ cand, size_t cand_frame, int *__restrict__ ncand, unsigned *__restrict__ shist,
            int ctr_stride)
@@ -198,21 +198,26 @@ k_orb_fast(const uint8_t *__restrict__ img, size_t frame_stride, int pitch, int 
         }
     }
     __syncthreads();
-    // (1) compass pre-test: a 9-arc of the 16-ring always holds two adjacent compass points
-    for (int i = tid; i < SCH * SCW; i += 256) {
-        const int r = i / SCW, q = i - r * SCW;            // score position (r, q) <-> pixel tile (r + 3, q + 3 + sh)
+    // (1) compass pre-test: a 9-arc of the 16-ring always holds two adjacent compass points, and every
+    // adjacent pair has one of {top, bottom} and one of {left, right}.  Score position (r, q) <-> pixel
+    // tile (r + 3, q + 3 + sh).  64 columns x 4 rows per pass (no index division), the last two columns after.
+    auto pretest = [&](int r, int q) {
         const int gy = oy - 1 + r, gx = ox - 1 + q;
         if (gy < lh - 3 && gx < lw - 3) {
             const int c = q + 3 + sh;
             const int v = px[r + 3][c];
-            const int d0 = v - px[r + 6][c], d4 = v - px[r + 3][c + 3], d8 = v - px[r][c], d12 = v - px[r + 3][c - 3];
-            const unsigned hi = (d0 > thr) | ((d4 > thr) << 1) | ((d8 > thr) << 2) | ((d12 > thr) << 3);
-            const unsigned lo = (d0 < -thr) | ((d4 < -thr) << 1) | ((d8 < -thr) << 2) | ((d12 < -thr) << 3);
-            const unsigned hh = hi & ((hi >> 1) | (hi << 3)), ll = lo & ((lo >> 1) | (lo << 3));
-            if ((hh | ll) & 0xfu) queue[atomicAdd(&qn, 1)] = (unsigned short)i;
+            const int d0 = v - px[r + 6][c], d8 = v - px[r][c];
+            const unsigned vhi = (d0 > thr) | ((d8 > thr) << 1), vlo = (d0 < -thr) | ((d8 < -thr) << 1);
+            if (vhi | vlo) {
+                const int d4 = v - px[r + 3][c + 3], d12 = v - px[r + 3][c - 3];
+                const bool hhi = (d4 > thr) | (d12 > thr), hlo = (d4 < -thr) | (d12 < -thr);
+                if ((vhi && hhi) || (vlo && hlo)) queue[atomicAdd(&qn, 1)] = (unsigned short)(r * SCW + q);
+            }
         }
         sc[r][q] = 0;
-    }
+    };
+    for (int r = tid >> 6; r < SCH; r += 4) pretest(r, tid & 63);
+    if (tid < 2 * SCH) pretest(tid >> 1, FTW + (tid & 1));
     __syncthreads();
     // (2) full strength of the survivors; ring offsets of cv2's FAST-9/16, clockwise from (0, 3)
     const int RX[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};

@@ -454,3 +454,39 @@ def test_multi_clip_sharding_on_device(vqa, ctx, small_clip):
     whole = SH.multi_clip_partials(SH.plan_clip_shards(lens, 1)[0], rows_of, lens, 0.8, ctx.ewm_partial)
     np.testing.assert_allclose(sum(p for p, _ in parts), whole[0], rtol=1e-6)
     assert np.array_equal(sum(i for _, i in parts), whole[1])
+
+
+def test_full_size_properties_1080p(ctx, synth):
+    """BASELINE.json configs[1]+[2] shapes at a length that spans several device chunks (48 frames): the
+    oracle is too slow here, so size-independent properties carry the check -- range splitting with a
+    halo and host/device input give identical rows, Parseval ties the tensor-core DCT energy to an exact
+    integer sum on every frame, histogram-derived entropies stay in range, PSNR/SSIM of a plane stack
+    against itself is inf / 1 and SSE is symmetric in its arguments."""
+    import torch
+    n = 100
+    clip = synth.synth_clip(n, 1080, 1920, seed=0)
+    full = ctx.complexity_frames(clip, 1920, 1080)
+    parts = np.concatenate([ctx.complexity_frames(clip[:37], 1920, 1080),
+                            ctx.complexity_frames(clip[37:], 1920, 1080, halo=clip[36])])
+    dev = ctx.complexity_frames(torch.from_numpy(clip).cuda(), 1920, 1080)
+    for f in full.dtype.names:
+        assert np.array_equal(parts[f], full[f], equal_nan=True), f
+        assert np.array_equal(dev[f], full[f], equal_nan=True), f
+    np.testing.assert_allclose(full["dct_energy"], full["gray_sq_sum"].astype(np.float64), rtol=3e-5)
+    sq = np.array([int((NO.bgr2gray(f).astype(np.int64) ** 2).sum()) for f in clip[::33]], dtype=np.uint64)
+    assert np.array_equal(full["gray_sq_sum"][::33], sq)
+    assert np.all((full["hist_entropy"] > 0) & (full["hist_entropy"] <= 8.0))
+    assert np.all((full["color_entropy"] > 0) & (full["color_entropy"] <= 24.0))
+    assert np.all((full["edge_count"] >= 0) & (full["edge_count"] <= 1080 * 1920))
+    assert np.all(np.isfinite(full["motion"][1:])) and np.all(full["motion"][1:] > 0)
+    assert np.all(full["temporal_dct"][1:] > 0)
+    # the synthetic clip pans 3 px / 2 px per frame: the mean flow magnitude sits near sqrt(13) on every pair
+    assert abs(float(np.median(full["motion"][1:])) - 13 ** 0.5) < 0.5
+    (ry, ru, rv), (dy, du, dv) = synth.synth_yuv_pairs(8, 1080, 1920, seed=1)
+    ab = ctx.psnr_ssim((dy, du, dv), (ry, ru, rv))
+    ba = ctx.psnr_ssim((ry, ru, rv), (dy, du, dv))
+    assert np.array_equal(ab["sse"], ba["sse"]) and np.array_equal(ab["psnr_avg"], ba["psnr_avg"])
+    np.testing.assert_allclose(ab["ssim_all"], ba["ssim_all"], rtol=1e-12)      # SSIM is symmetric too
+    same = ctx.psnr_ssim((dy, du, dv), (dy, du, dv))
+    assert np.all(np.isinf(same["psnr_avg"])) and np.all(same["sse"] == 0) and np.allclose(same["ssim_all"], 1.0)
+    assert np.all((ab["ssim_all"] > 0) & (ab["ssim_all"] < 1)) and np.all(ab["psnr_avg"] > 20)
