@@ -159,3 +159,45 @@ def test_multi_clip_partials_equal_per_clip_single_pass(vqa):
         for si, name in enumerate(SH.SERIES):
             x = np.asarray(tables[c][name][SH.FIRST[name]:], dtype=np.float64)
             assert want_p[c, si] == pytest.approx(NO.smoothed_mean(x, 0.8), rel=1e-12)
+
+
+def _multi_worker(rank, world, port, clips, out_path):
+    import torch.distributed as dist
+    import rtvqa_b200
+    from rtvqa_b200 import _native as N
+    from rtvqa_b200 import sharding as SH
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lens = [len(c) for c in clips]
+    plan = SH.plan_clip_shards(lens, world)[rank]
+
+    def rows_of(clip, a, b):
+        return _rows_from_oracle(clips[clip][a:b], a, clips[clip][a - 1] if a > 0 else None, 64, 64, N.FRAME_DTYPE)
+
+    partials, ints = SH.multi_clip_partials(plan, rows_of, lens, 0.8, _host_partial)
+    partials, ints = SH.reduce_partials(partials, ints)
+    if rank == 0:
+        np.save(out_path, np.concatenate([partials.ravel(), ints.ravel().astype(np.float64)]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("cuts", [((0, 5), (5, 8), (8, 12)), ((0, 9),)])
+def test_two_rank_gloo_multi_clip_reduce(vqa, small_clip, tmp_path, cuts):
+    """BASELINE config 5 over 2 gloo ranks: three clips placed whole (clips >= ranks) and one clip cut
+    into frame ranges with a halo (clips < ranks); ONE all-reduce of [n_clips x 7] closes the batch and
+    every clip's means equal the reference-shaped single pass."""
+    import torch.multiprocessing as mp
+    from rtvqa_b200 import sharding as SH
+    clips = [small_clip[a:b] for a, b in cuts]
+    out = str(tmp_path / "multi.npy")
+    mp.spawn(_multi_worker, args=(2, _free_port(), clips, out), nprocs=2, join=True)
+    got = np.load(out)
+    n = len(clips)
+    partials, ints = got[:n * len(SH.SERIES)].reshape(n, -1), got[n * len(SH.SERIES):].reshape(n, 3)
+    for c, clip in enumerate(clips):
+        want = RP.average_scene_complexity(clip, 64, 64, frame_interval=1)
+        res = SH.finalize(partials[c], len(clip), want[7])
+        np.testing.assert_allclose(res, want, rtol=1e-6)
+        assert ints[c, 0] == sum(RP.o_edge(f, 64, 64) for f in clip[1:]) and ints[c, 2] == len(clip)
