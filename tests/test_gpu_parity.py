@@ -490,3 +490,25 @@ def test_full_size_properties_1080p(ctx, synth):
     same = ctx.psnr_ssim((dy, du, dv), (dy, du, dv))
     assert np.all(np.isinf(same["psnr_avg"])) and np.all(same["sse"] == 0) and np.allclose(same["ssim_all"], 1.0)
     assert np.all((ab["ssim_all"] > 0) & (ab["ssim_all"] < 1)) and np.all(ab["psnr_avg"] > 20)
+
+
+def test_config1_reference_case_on_device(ctx, golden, synth):
+    """BASELINE.json configs[0] (300 x 1080p, frame_interval 10, resize 64x64) through the C ABI against
+    the 8-tuple the UNMODIFIED reference returned for this clip (tests/golden, c1_avg)."""
+    from helpers import config1_sampled_frames
+    from rtvqa_b200 import sharding as SH
+    frames = config1_sampled_frames(synth)
+    clip = np.stack([frames[i] for i in sorted(frames)])
+    assert hashlib.sha256(clip.tobytes()).hexdigest() == golden["c1_sha_sampled"]
+    rows = ctx.complexity_frames(clip, 64, 64)
+    ts = [1000.0 * i / 30.0 for i in range(0, 300, 10)]
+    fps = ctx.framerate_series(ts)
+    got = [ctx.ewm_partial(np.asarray(rows[name][SH.FIRST[name]:], dtype=np.float64), 0, None, 0.8) for name in SH.SERIES]
+    got.append(ctx.ewm_partial(fps, 0, None, 0.8))
+    want = golden["c1_avg"]                                   # motion, dct, hist, edge, orb, colour, temporal dct, framerate
+    order = {"motion": 0, "dct_energy": 1, "hist_entropy": 2, "edge_count": 3, "orb_count": 4, "color_entropy": 5,
+             "temporal_dct": 6}
+    for name, g in zip(SH.SERIES, got[:-1]):
+        tol = 1e-12 if name in ("edge_count", "orb_count") else RTOL
+        assert g == pytest.approx(want[order[name]], rel=tol), name
+    assert got[-1] == pytest.approx(want[7], rel=1e-13)

@@ -101,3 +101,19 @@ def test_psnr_ssim_known_answers(synth):
         assert b["ssim_all"] == pytest.approx(r["ssim_all"][i], rel=1e-6)
     # ssim constants (vf_ssim.c): c1 = .01^2*255^2*64, c2 = .03^2*255^2*64*63
     assert int(.01 * .01 * 255 * 255 * 64 + .5) == 416 and int(.03 * .03 * 255 * 255 * 64 * 63 + .5) == 235963
+
+
+def test_config1_reference_case(golden, synth):
+    """BASELINE.json configs[0] -- the reference's own CPU-runnable case (300 x 1080p, frame_interval 10,
+    resize 64x64): the oracle port against the 8-tuple the UNMODIFIED reference returned for it."""
+    import numpy as np
+    from helpers import SparseClip, config1_sampled_frames
+    frames = config1_sampled_frames(synth)
+    idx = sorted(frames)
+    assert idx == list(range(9, 300, 10))
+    assert _sha(np.stack([frames[i] for i in idx])) == golden["c1_sha_sampled"], "synthetic generator drifted"
+    got = RP.average_scene_complexity(SparseClip(300, frames), 64, 64, frame_interval=10, workers=4)
+    want = golden["c1_avg"]
+    np.testing.assert_allclose(got, want, rtol=1e-4)
+    assert got[3] == pytest.approx(want[3], rel=1e-12) and got[4] == pytest.approx(want[4], rel=1e-12)   # edge, ORB: exact series
+    assert got[7] == pytest.approx(3.0000000000000004, rel=1e-15)          # README.md:72 framerate of a CFR 30 fps clip at I = 10
