@@ -75,7 +75,9 @@ typedef struct vqa_orb_cfg {
 
 /* One detected keypoint (cv2.KeyPoint fields that exist before orientation / descriptors). */
 typedef struct vqa_keypoint {
-    float x, y;               /* level-0 coordinates: level coordinates * scale_factor^octave */
+    float x, y;               /* cv2.KeyPoint.pt: level coordinates * (float)pow(scale_factor, octave) */
+    float size;               /* cv2.KeyPoint.size: patch size 31 * level scale */
+    float angle;              /* cv2.KeyPoint.angle: intensity-centroid orientation in degrees (orb.cpp ICAngles, fastAtan2) */
     float response;           /* Harris response (orb.cpp HarrisResponses), bit-exact */
     int32_t octave;           /* pyramid level */
     int32_t lx, ly;           /* integer coordinates inside the level image */

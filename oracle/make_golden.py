@@ -145,7 +145,9 @@ def orb_general(gray, **kw):
     per = [sum(1 for k in kps if k.octave == l) for l in range(nl)]
     rr = np.array(sorted((k.octave, float(np.float32(k.response))) for k in kps), dtype=np.float64).reshape(-1, 2)
     key = np.concatenate([rr[:, 0].astype(np.int32).view(np.uint8), rr[:, 1].astype(np.float32).view(np.uint8)])
-    return dict(count=len(kps), per_level=per, digest=sha(key))
+    # every cv2.KeyPoint field: (octave, pt.x, pt.y, size, angle, response), sorted, float32 bit patterns
+    full = np.array(sorted((k.octave, k.pt[0], k.pt[1], k.size, k.angle, k.response) for k in kps), dtype=np.float32).reshape(-1, 6)
+    return dict(count=len(kps), per_level=per, digest=sha(key), digest_keypoints=sha(full))
 
 
 ORB_CONFIGS = {
@@ -153,6 +155,7 @@ ORB_CONFIGS = {
     "n1000": dict(nfeatures=1000),
     "n200_l4_s15": dict(nfeatures=200, nlevels=4, scaleFactor=1.5),
     "edge16_fast10": dict(edgeThreshold=16, fastThreshold=10),
+    "edge8": dict(edgeThreshold=8),                      # orientation patches reach into the reflect-101 border
 }
 
 

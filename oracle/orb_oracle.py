@@ -149,6 +149,97 @@ def orb_detect(gray: np.ndarray, nfeatures: int = NFEATURES, nlevels: int = NLEV
     return rows, per_level
 
 
+# ----------------------------------------------------------------------------- orientation (ICAngles)
+PATCH_SIZE = 31
+HALF_PATCH = PATCH_SIZE // 2
+
+
+def umax_table(half: int = HALF_PATCH):
+    """orb.cpp computeKeyPoints: half-width of the circular patch per row offset v,
+    [15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3] for patchSize 31."""
+    umax = [0] * (half + 2)
+    vmax = int(np.floor(half * np.sqrt(2.0) / 2 + 1))
+    vmin = int(np.ceil(half * np.sqrt(2.0) / 2))
+    for v in range(vmax + 1):
+        umax[v] = int(np.rint(np.sqrt(float(half * half - v * v))))
+    v0 = 0
+    for v in range(half, vmin - 1, -1):
+        while umax[v0] == umax[v0 + 1]:
+            v0 += 1
+        umax[v] = v0
+        v0 += 1
+    return umax[:half + 1]
+
+
+_F = np.float32
+_RAD = _F(180.0 / np.pi)
+ATAN_P1, ATAN_P3 = _F(0.9997878412794807) * _RAD, _F(-0.3258083974640975) * _RAD
+ATAN_P5, ATAN_P7 = _F(0.1555786518463281) * _RAD, _F(-0.04432655554792128) * _RAD
+ATAN_EPS = _F(2.220446049250313e-16)
+
+
+def fast_atan2(y, x) -> np.float32:
+    """core/mathfuncs_core fastAtan2 (degrees, odd degree-7 polynomial), float32, no contraction."""
+    y, x = _F(y), _F(x)
+    ax, ay = abs(x), abs(y)
+    if ax >= ay:
+        c = ay / (ax + ATAN_EPS)
+        c2 = c * c
+        a = (((ATAN_P7 * c2 + ATAN_P5) * c2 + ATAN_P3) * c2 + ATAN_P1) * c
+    else:
+        c = ax / (ay + ATAN_EPS)
+        c2 = c * c
+        a = _F(90.0) - (((ATAN_P7 * c2 + ATAN_P5) * c2 + ATAN_P3) * c2 + ATAN_P1) * c
+    if x < 0:
+        a = _F(180.0) - a
+    if y < 0:
+        a = _F(360.0) - a
+    return _F(a)
+
+
+def _reflect101(i: int, n: int) -> int:
+    while i < 0 or i >= n:
+        i = -i if i < 0 else 2 * n - 2 - i
+    return i
+
+
+def ic_angle(img: np.ndarray, x: int, y: int, umax=None) -> np.float32:
+    """orb.cpp ICAngles: intensity-centroid orientation over the circular patch of radius 15; pixels
+    outside the level image come from its BORDER_REFLECT_101 extension (only reachable when
+    edgeThreshold < 16)."""
+    umax = umax or umax_table()
+    h, w = img.shape
+    half = len(umax) - 1
+
+    def P(yy, xx):
+        return int(img[_reflect101(yy, h), _reflect101(xx, w)])
+
+    m01 = m10 = 0
+    for u in range(-half, half + 1):
+        m10 += u * P(y, x + u)
+    for v in range(1, half + 1):
+        d, vs = umax[v], 0
+        for u in range(-d, d + 1):
+            vp, vm = P(y + v, x + u), P(y - v, x + u)
+            vs += vp - vm
+            m10 += u * (vp + vm)
+        m01 += v * vs
+    return fast_atan2(_F(m01), _F(m10))
+
+
+def orb_keypoints(gray: np.ndarray, **kw):
+    """cv2.KeyPoint fields of ORB's keypoints as rows (octave, pt.x, pt.y, size, angle, response): level
+    coordinates times the float32 level scale, size = 31 * scale, ICAngles orientation."""
+    nlevels, sf = kw.get("nlevels", NLEVELS), kw.get("scale_factor", SCALE_FACTOR)
+    rows, _ = orb_detect(gray, **kw)
+    pyr, scales, um = pyramid(gray, nlevels, sf), level_scales(nlevels, sf), umax_table()
+    out = []
+    for l, x, y, r, _s in rows:
+        sc = scales[l]
+        out.append((l, float(_F(x) * sc), float(_F(y) * sc), float(_F(PATCH_SIZE) * sc), float(ic_angle(pyr[l], x, y, um)), r))
+    return out
+
+
 def orb_count(gray: np.ndarray, **kw) -> int:
     """len(cv2.ORB_create(**kw).detectAndCompute(gray, None)[0])"""
     return sum(orb_detect(gray, **kw)[1])

@@ -48,7 +48,7 @@ def orb_cfg(nfeatures=500, scale_factor=1.2, nlevels=8, edge_threshold=31, fast_
     return OrbCfg(int(nfeatures), int(nlevels), int(edge_threshold), int(fast_threshold), float(scale_factor))
 
 
-KEYPOINT_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("response", "<f4"), ("octave", "<i4"), ("lx", "<i4"),
+KEYPOINT_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"), ("octave", "<i4"), ("lx", "<i4"),
                            ("ly", "<i4"), ("fast_score", "<i4")], align=True)
 ORB_MAX_LEVELS = 16
 

@@ -24,6 +24,7 @@ constexpr int MAXL = 16;
 struct OrbLevels {                       // passed by value to the kernels
     int nlevels;
     int lh[MAXL], lw[MAXL], pitch[MAXL], quota[MAXL];
+    float scale[MAXL];                   // orb.cpp getScale: (float)pow((double)scaleFactor, level)
     unsigned long long pyr_off[MAXL];    // byte offset of level l >= 1 inside one frame's pyramid block
     unsigned long long cand_off[MAXL];   // entry offset of level l inside one frame's candidate block
 };
@@ -50,6 +51,7 @@ void orb_geometry(int h, int w, const vqa_orb_cfg &cfg, OrbGeom &g)
     size_t pyr = 0, cand = 0, taps = 0;
     for (int l = 0; l < cfg.nlevels; l++) {
         const float sc = (float)pow(sfd, (double)l);
+        L.scale[l] = sc;
         volatile float fw = (float)w / sc, fh = (float)h / sc;
         L.lw[l] = (int)lrint((double)fw);
         L.lh[l] = (int)lrint((double)fh);
@@ -342,7 +344,7 @@ __device__ __forceinline__ uint32_t order_key(float f)     // larger float <=> l
 __global__ void __launch_bounds__(256)
 k_orb_select(OrbLevels L, const float *__restrict__ resp, const uint32_t *__restrict__ rpos, size_t cand_frame,
              const int *__restrict__ nresp, int *__restrict__ counts, int *__restrict__ level_counts,
-             vqa_keypoint *__restrict__ kps, int kp_cap, float sf)
+             vqa_keypoint *__restrict__ kps, int kp_cap)
 {
     __shared__ int hist[256];
     __shared__ uint32_t s_prefix;
@@ -395,15 +397,17 @@ k_orb_select(OrbLevels L, const float *__restrict__ resp, const uint32_t *__rest
                     const int o = atomicAdd(&s_out, 1);
                     if (o < kp_cap) {
                         const uint32_t e = p[i];
-                        const float scale = powf(sf, (float)l);   // display only; the level coordinates are exact
+                        const float scale = L.scale[l];
                         vqa_keypoint k;
                         k.lx = (int)(e & 0xfff);
                         k.ly = (int)((e >> 12) & 0xfff);
                         k.octave = l;
                         k.fast_score = (int)(e >> 24);
                         k.response = v;
-                        k.x = (float)k.lx * scale;
-                        k.y = (float)k.ly * scale;
+                        k.x = __fmul_rn((float)k.lx, scale);            // computeKeyPoints: pt *= scale
+                        k.y = __fmul_rn((float)k.ly, scale);
+                        k.size = __fmul_rn(31.f, scale);                // patchSize * scale
+                        k.angle = -1.f;                                 // filled by k_orb_angle
                         kps[(size_t)frame * kp_cap + o] = k;
                     }
                 }
@@ -417,6 +421,70 @@ k_orb_select(OrbLevels L, const float *__restrict__ resp, const uint32_t *__rest
         __syncthreads();
     }
     if (tid == 0) counts[frame] = total;
+}
+
+// orb.cpp ICAngles: orientation of a keypoint = fastAtan2(m01, m10) of the intensity moments over the
+// circular patch of radius 15 (row half-widths umax[v]); pixels outside the level image come from its
+// reflect-101 border (only reachable when edgeThreshold < 16).  One warp per keypoint, lane v (< 16)
+// owns the row pair +-v; integer moments, float32 polynomial in OpenCV's evaluation order.
+__device__ __forceinline__ int reflect101(int i, int n)
+{
+    while (i < 0 || i >= n) i = i < 0 ? -i : 2 * n - 2 - i;
+    return i;
+}
+
+__device__ __forceinline__ float fast_atan2_deg(float y, float x, float p1, float p3, float p5, float p7)
+{
+    const float ax = fabsf(x), ay = fabsf(y), eps = 2.220446049250313e-16f;
+    const bool flat = ax >= ay;
+    const float c = flat ? __fdiv_rn(ay, __fadd_rn(ax, eps)) : __fdiv_rn(ax, __fadd_rn(ay, eps));
+    const float c2 = __fmul_rn(c, c);
+    float a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+    if (!flat) a = __fsub_rn(90.f, a);
+    if (x < 0.f) a = __fsub_rn(180.f, a);
+    if (y < 0.f) a = __fsub_rn(360.f, a);
+    return a;
+}
+
+__global__ void __launch_bounds__(256)
+k_orb_angle(OrbLevels L, const uint8_t *__restrict__ img0, size_t frame_stride0, const uint8_t *__restrict__ pyr,
+            size_t pyr_frame, const int *__restrict__ counts, vqa_keypoint *__restrict__ kps, int kp_cap,
+            float p1, float p3, float p5, float p7)
+{
+    const int UMAX[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+    const int frame = blockIdx.y, lane = threadIdx.x & 31, ki = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (ki >= min(counts[frame], kp_cap)) return;                       // warp-uniform
+    vqa_keypoint *kp = kps + (size_t)frame * kp_cap + ki;
+    const int l = kp->octave, x = kp->lx, y = kp->ly, lw = L.lw[l], lh = L.lh[l], pitch = L.pitch[l];
+    const uint8_t *img = l == 0 ? img0 + (size_t)frame * frame_stride0 : pyr + (size_t)frame * pyr_frame + L.pyr_off[l];
+    const bool inside = x >= 15 && y >= 15 && x + 15 < lw && y + 15 < lh;
+    int m01 = 0, m10 = 0;
+    if (lane < 16) {
+        const int v = lane, d = UMAX[v];
+        if (inside) {
+            const uint8_t *rp = img + (size_t)(y + v) * pitch + x, *rm = img + (size_t)(y - v) * pitch + x;
+            int vs = 0;
+            for (int u = -d; u <= d; u++) {
+                const int vp = rp[u], vm = rm[u];
+                vs += vp - vm;
+                m10 += u * (v ? vp + vm : vp);
+            }
+            m01 = v * vs;
+        } else {
+            const uint8_t *rp = img + (size_t)reflect101(y + v, lh) * pitch, *rm = img + (size_t)reflect101(y - v, lh) * pitch;
+            int vs = 0;
+            for (int u = -d; u <= d; u++) {
+                const int xx = reflect101(x + u, lw);
+                const int vp = rp[xx], vm = rm[xx];
+                vs += vp - vm;
+                m10 += u * (v ? vp + vm : vp);
+            }
+            m01 = v * vs;
+        }
+    }
+    m01 = warp_sum(m01);
+    m10 = warp_sum(m10);
+    if (lane == 0) kp->angle = fast_atan2_deg((float)m01, (float)m10, p1, p3, p5, p7);
 }
 
 }  // namespace
@@ -515,8 +583,15 @@ int run_orb_general(vqa_ctx *c, const uint8_t *gray, int n, int h, int w, size_t
         VQA_LAUNCH(c, k_orb_harris, dim3(16, live, n), 128, 0, L, gray, frame_stride, pyr, g->pyr_frame, cand,
                    g->cand_frame, ncand, cut, resp, rpos, nresp, s4);
     }
-    VQA_LAUNCH(c, k_orb_select, n, 256, 0, L, resp, rpos, g->cand_frame, nresp, counts, level_counts, kps, kp_cap,
-               cfg.scale_factor);
+    VQA_LAUNCH(c, k_orb_select, n, 256, 0, L, resp, rpos, g->cand_frame, nresp, counts, level_counts, kps, kp_cap);
+    if (kps && live > 0) {
+        // mathfuncs_core fastAtan2 coefficients, formed in float exactly as OpenCV's translation unit does
+        const float rad = (float)(180.0 / 3.1415926535897932384626433832795);
+        const float p1 = 0.9997878412794807f * rad, p3 = -0.3258083974640975f * rad;
+        const float p5 = 0.1555786518463281f * rad, p7 = -0.04432655554792128f * rad;
+        VQA_LAUNCH(c, k_orb_angle, dim3(cdiv(kp_cap, 8), n), 256, 0, L, gray, frame_stride, pyr, g->pyr_frame, counts, kps,
+                   kp_cap, p1, p3, p5, p7);
+    }
     return VQA_OK;
 }
 

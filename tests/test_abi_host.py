@@ -54,8 +54,8 @@ int main(void) {
   printf("%zu %zu %zu\\n", sizeof(vqa_cfg), offsetof(vqa_cfg, orb_width), offsetof(vqa_cfg, orb_height));
   printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(vqa_orb_cfg), offsetof(vqa_orb_cfg, nfeatures), offsetof(vqa_orb_cfg, nlevels),
     offsetof(vqa_orb_cfg, edge_threshold), offsetof(vqa_orb_cfg, fast_threshold), offsetof(vqa_orb_cfg, scale_factor));
-  printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(vqa_keypoint), offsetof(vqa_keypoint, x), offsetof(vqa_keypoint, y),
-    offsetof(vqa_keypoint, response), offsetof(vqa_keypoint, octave), offsetof(vqa_keypoint, lx), offsetof(vqa_keypoint, ly),
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(vqa_keypoint), offsetof(vqa_keypoint, x), offsetof(vqa_keypoint, y),
+    offsetof(vqa_keypoint, size), offsetof(vqa_keypoint, angle), offsetof(vqa_keypoint, response), offsetof(vqa_keypoint, octave), offsetof(vqa_keypoint, lx), offsetof(vqa_keypoint, ly),
     offsetof(vqa_keypoint, fast_score));
   return 0; }''')
     exe = tmp_path / "layout"

@@ -13,7 +13,7 @@ from oracle import orb_oracle as OO
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CFGS = {"default": {}, "n1000": dict(nfeatures=1000), "n200_l4_s15": dict(nfeatures=200, nlevels=4, scale_factor=1.5),
-        "edge16_fast10": dict(edge_threshold=16, fast_threshold=10)}
+        "edge16_fast10": dict(edge_threshold=16, fast_threshold=10), "edge8": dict(edge_threshold=8)}
 
 
 def _sha(a):
@@ -53,14 +53,22 @@ def digest(rows):
     return _sha(key)
 
 
+def digest_keypoints(rows):
+    """sha of the sorted (octave, pt.x, pt.y, size, angle, response) float32 table (make_golden.py)."""
+    return _sha(np.array(sorted(rows), dtype=np.float32).reshape(-1, 6))
+
+
 def test_orb_oracle_matches_cv2_fixtures(orb_golden, small_clip, synth):
-    assert len(orb_golden["cases"]) >= 30
+    assert len(orb_golden["cases"]) >= 37
     for case in orb_golden["cases"]:
         gray = golden_gray(case, small_clip, synth)
         rows, per = OO.orb_detect(gray, **CFGS[case["cfg"]])
         assert per == case["per_level"], (case["clip"], case["frame"], case["cfg"])
         assert len(rows) == case["count"]
         assert digest(rows) == case["digest"], "Harris responses are not bit-identical to cv2's"
+        if case["clip"] != "hd":                  # every cv2.KeyPoint field incl. the orientation (pure-Python loops: skip 1080p)
+            assert digest_keypoints(OO.orb_keypoints(gray, **CFGS[case["cfg"]])) == case["digest_keypoints"], \
+                (case["clip"], case["frame"], case["cfg"])
 
 
 def test_orb_at_64x64_is_the_reference_path(small_clip):
@@ -69,6 +77,15 @@ def test_orb_at_64x64_is_the_reference_path(small_clip):
     for f in small_clip:
         g = NO.bgr2gray(NO.resize_linear_u8(f, 64, 64))
         assert OO.orb_count(g) == CO.orb_count_64(g)
+
+
+def test_orientation_known_answers():
+    assert OO.umax_table() == [15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3]
+    assert OO.fast_atan2(0, 0) == 0 and OO.fast_atan2(0, 5) == 0
+    assert abs(float(OO.fast_atan2(3, 3)) - 45) < 0.01 and abs(float(OO.fast_atan2(-2, 0)) - 270) < 0.01
+    ramp = np.tile(np.arange(64, dtype=np.uint8) * 3, (64, 1))          # brighter to the right: centroid at +x, angle 0
+    assert OO.ic_angle(ramp, 32, 32) == 0
+    assert abs(float(OO.ic_angle(np.ascontiguousarray(ramp.T), 32, 32)) - 90) < 0.01
 
 
 def test_retain_best_keeps_ties():

@@ -6,7 +6,7 @@ import pytest
 
 from oracle import np_oracle as NO
 from oracle import orb_oracle as OO
-from test_orb_cpu import CFGS, digest, golden_gray, orb_golden  # noqa: F401  (fixture re-export)
+from test_orb_cpu import CFGS, digest, digest_keypoints, golden_gray, orb_golden  # noqa: F401  (fixture re-export)
 
 pytestmark = pytest.mark.gpu
 
@@ -56,6 +56,10 @@ def test_keypoints_match_cv2_fixtures(ctx, orb_golden, small_clip, synth):
         assert int(counts[0]) == case["count"], tag
         assert levels[0, :len(case["per_level"])].tolist() == case["per_level"], tag
         assert digest([(int(k["octave"]), 0, 0, float(k["response"])) for k in kps[0]]) == case["digest"], tag
+        # every cv2.KeyPoint field (pt, size, angle, response, octave), float32 bit patterns
+        full = [(int(k["octave"]), float(k["x"]), float(k["y"]), float(k["size"]), float(k["angle"]), float(k["response"]))
+                for k in kps[0]]
+        assert digest_keypoints(full) == case["digest_keypoints"], tag
 
 
 @pytest.mark.parametrize("h,w,kind", [(96, 128, "clip"), (270, 480, "clip"), (200, 333, "noise"), (150, 150, "blur"),
@@ -75,10 +79,10 @@ def test_keypoint_sets_match_oracle(ctx, synth, h, w, kind):
     rows, per = OO.orb_detect(g)
     assert levels[0, :8].tolist() == per and int(counts[0]) == sum(per)
     assert _rows(kps[0]) == _oracle_rows(rows)
-    # level-0 coordinates as cv2 reports them
-    for k in kps[0][:20]:
-        s = np.float32(1.2) ** np.float32(int(k["octave"]))
-        assert k["x"] == pytest.approx(float(k["lx"]) * float(s), rel=1e-5)
+    want = sorted(OO.orb_keypoints(g))
+    got = sorted((int(k["octave"]), float(k["x"]), float(k["y"]), float(k["size"]), float(k["angle"]), float(k["response"]))
+                 for k in kps[0])
+    assert got == want                                                  # pt, size, orientation, response: exact
 
 
 def test_batches_device_input_and_flat_frames(ctx, synth):
