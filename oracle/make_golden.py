@@ -186,8 +186,28 @@ def main_orb():
     print("wrote orb_general.json:", len(g["cases"]), "cases")
 
 
+def main_fr():
+    """tests/golden/psnr_cv2.json: per-plane PSNR of synthetic yuv420p pairs from an independent library
+    (cv2.PSNR).  FFmpeg itself is not in the image, so this pins the PSNR half of a13 only as far as
+    10*log10(255^2 / mse) per plane goes; the area-weighted average and SSIM stay on known answers."""
+    import cv2
+    S = _load_synth()
+    g = dict(meta=dict(cv2=cv2.__version__, source="cv2.PSNR(main_plane, ref_plane) (R = 255)"), cases=[])
+    for (n, h, w, seed) in ((3, 72, 96, 2), (2, 270, 480, 1), (1, 1080, 1920, 1)):
+        ref, dist = S.synth_yuv_pairs(n, h, w, seed=seed)
+        for i in range(n):
+            g["cases"].append(dict(n=n, h=h, w=w, seed=seed, frame=i,
+                                   plane_sha=[sha(dist[c][i]) for c in range(3)],
+                                   psnr=[float(cv2.PSNR(dist[c][i], ref[c][i])) for c in range(3)]))
+    with open(os.path.join(GOLD, "psnr_cv2.json"), "w") as f:
+        json.dump(g, f, indent=1)
+    print("wrote psnr_cv2.json:", len(g["cases"]), "cases")
+
+
 if __name__ == "__main__":
-    if "--orb" in sys.argv:
+    if "--fr" in sys.argv:
+        main_fr()
+    elif "--orb" in sys.argv:
         main_orb()
     else:
         main()

@@ -117,3 +117,23 @@ def test_config1_reference_case(golden, synth):
     np.testing.assert_allclose(got, want, rtol=1e-4)
     assert got[3] == pytest.approx(want[3], rel=1e-12) and got[4] == pytest.approx(want[4], rel=1e-12)   # edge, ORB: exact series
     assert got[7] == pytest.approx(3.0000000000000004, rel=1e-15)          # README.md:72 framerate of a CFR 30 fps clip at I = 10
+
+
+def test_psnr_planes_against_cv2_fixture(synth):
+    """a13, PSNR half: per-plane PSNR of the oracle against cv2.PSNR values (tests/golden/psnr_cv2.json).
+    SSIM and the plane weighting remain on known answers only (no FFmpeg in the image: parity unpinned)."""
+    import json, os
+    from conftest import GOLD
+    with open(os.path.join(GOLD, "psnr_cv2.json")) as f:
+        g = json.load(f)
+    cache = {}
+    for case in g["cases"]:
+        key = (case["n"], case["h"], case["w"], case["seed"])
+        if key not in cache:
+            cache[key] = synth.synth_yuv_pairs(*key[:3], seed=key[3])
+        ref, dist = cache[key]
+        i = case["frame"]
+        assert [_sha(dist[c][i]) for c in range(3)] == case["plane_sha"]
+        got = RP.psnr_ssim_frames(tuple(p[i:i + 1] for p in dist), tuple(p[i:i + 1] for p in ref))
+        psnr = 10.0 * np.log10(255.0 * 255.0 / got["mse"][0])
+        np.testing.assert_allclose(psnr, case["psnr"], rtol=1e-12)
