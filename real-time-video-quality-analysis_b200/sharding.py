@@ -77,6 +77,39 @@ def reduce_partials(partials: np.ndarray, int_totals: np.ndarray, group=None, de
     return f.cpu().numpy(), i.cpu().numpy()
 
 
+def gather_rows(rows, group=None, device=None):
+    """Verification alternative of SURVEY.md 8(e): all-gather the per-frame table (K x 7 doubles) so that
+    any rank can run the reference's own smoothing on the whole series.  Returns the concatenated
+    [K, len(SERIES)] float64 table in rank order (ranks own contiguous, ordered frame ranges)."""
+    import torch
+    import torch.distributed as dist
+    table = np.stack([np.asarray(rows[name], dtype=np.float64) for name in SERIES], axis=1) if len(rows) \
+        else np.zeros((0, len(SERIES)))
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return table
+    world = dist.get_world_size(group)
+    dev = device if device is not None else ("cuda" if dist.get_backend(group) == "nccl" else "cpu")
+    n = torch.tensor([len(table)], dtype=torch.int64, device=dev)
+    counts = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(counts, n, group=group)
+    counts = [int(c.item()) for c in counts]
+    pad = torch.zeros((max(counts + [1]), len(SERIES)), dtype=torch.float64, device=dev)
+    pad[:len(table)] = torch.as_tensor(table, dtype=torch.float64, device=dev)
+    parts = [torch.zeros_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad, group=group)
+    return np.concatenate([p[:c].cpu().numpy() for p, c in zip(parts, counts)], axis=0)
+
+
+def means_from_table(table: np.ndarray, alpha: float, smooth_fn):
+    """The reference's reduction on a gathered table: np.mean(smooth_data(series)) per column
+    (complexity_metrics.py:301-310) with the series starts of App. B; ``smooth_fn(x, alpha)`` -> array."""
+    out = []
+    for si, name in enumerate(SERIES):
+        x = table[FIRST[name]:, si]
+        out.append(float(np.mean(smooth_fn(x, alpha))) if len(x) else (0.0 if name == "temporal_dct" else float("nan")))
+    return out
+
+
 def finalize(partials: np.ndarray, k_frames: int, framerate_mean: float):
     """8-tuple in the reference's order; empty series -> nan (temporal DCT -> 0.0)."""
     vals = []

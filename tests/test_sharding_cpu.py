@@ -54,8 +54,11 @@ def _worker(rank, world, port, clip, out_path):
     ts = 1000.0 * np.arange(k) / 30.0
     fps = [NO.process_frame_interval_for_parallel((x, y)) for x, y in zip(ts[:-1], ts[1:])]
     res = SH.finalize(partials, k, NO.smoothed_mean(fps, 0.8))
+    # verification alternative: all-gather the per-frame table, smooth the whole series
+    table = SH.gather_rows(rows)
+    gathered = SH.means_from_table(table, 0.8, NO.ewm_mean)
     if rank == 0:
-        np.save(out_path, np.array(list(res) + [float(v) for v in ints]))
+        np.save(out_path, np.array(list(res) + [float(v) for v in ints] + gathered + [float(len(table))]))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -83,6 +86,9 @@ def test_two_rank_gloo_reduce_matches_single_pass(vqa, small_clip, golden, tmp_p
     np.testing.assert_allclose(got[:8], want, rtol=1e-6)
     edges = [RP.o_edge(f, 64, 64) for f in clip[1:]]
     assert got[8] == sum(edges) and got[10] == len(clip)          # integer totals identical for any rank count
+    # (3) the all-gather + whole-series smoothing path agrees with the partial-sum all-reduce to <= 1e-12
+    assert got[18] == len(clip)
+    np.testing.assert_allclose(got[11:18], got[:7], rtol=1e-12)
 
 
 @pytest.mark.parametrize("k,world", [(30, 1), (30, 2), (30, 4), (30, 8), (7, 8), (299, 8)])
