@@ -858,13 +858,16 @@ int run_farneback(vqa_ctx *c, const uint8_t *gray, int npairs, int h, int w, dou
         }
         // rows per block of the marching blur: long strips amortise the 15-row warm-up, but the small
         // pyramid levels need shorter strips to put >= ~3 waves of blocks on 148 SMs x 8 blocks
-        int rows_pb = MS_H;
+        // VQA_MS_H: cap of the strip height (A/B knob, read per call; default MS_H)
+        const char *msh_env = getenv("VQA_MS_H");
+        const int ms_h_cap = (msh_env && atoi(msh_env) >= 16) ? atoi(msh_env) : MS_H;
+        int rows_pb = ms_h_cap;
         {
             const long want = 3L * c->sm_count * 8, per_row_strip = (long)cdiv(lw, MS_OUT) * npairs;
             const long strips = (want + per_row_strip - 1) / per_row_strip;
             if (strips > 0) rows_pb = (int)((lh + strips - 1) / strips);
             if (rows_pb < 16) rows_pb = 16;
-            if (rows_pb > MS_H) rows_pb = MS_H;
+            if (rows_pb > ms_h_cap) rows_pb = ms_h_cap;
         }
         float *Mcur = M, *Mnxt = nullptr;
         if (fuse_epi) { VQA_BUF(c, M2, float, "fb.M2", m_pair * npairs); Mnxt = M2; }
