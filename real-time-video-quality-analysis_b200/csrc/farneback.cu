@@ -380,12 +380,32 @@ k_fb_polyexp(const float *__restrict__ I, int h, int w, PolyConst pc, float *__r
 // flow_k(x, y) = 2 * resize_f32(flow_{k+1}) (INTER_LINEAR upscale, OpenCV float tap rules).  The
 // up-sampled flow is consumed only by the first UpdateMatrices of a level (the box-blur solve then
 // rewrites the whole field), so it is evaluated on the fly there and never stored.
+// lin_tap_f32 for an exact 2x up-scale (dn == 2 * sn), in integer arithmetic: (d + 0.5) * 0.5 - 0.5 =
+// d / 2 - 0.25, so floor = (d - 1) >> 1 and the fraction is 0.75 for even d, 0.25 for odd d -- the same
+// numbers the double-precision form produces (every intermediate is exact), without its FP64 work.
+__device__ __forceinline__ void up2_tap_f32(int d, int sn, bool vertical, int &i0, int &i1, float &a)
+{
+    int i = (d - 1) >> 1;
+    a = (d & 1) ? 0.25f : 0.75f;
+    if (!vertical) {
+        if (i < 0) { i = 0; a = 0.f; }
+        if (i >= sn - 1) { i = sn - 1; a = 0.f; }
+    }
+    i0 = clampi(i, 0, sn - 1);
+    i1 = clampi(i + 1, 0, sn - 1);
+}
+
 __device__ __forceinline__ float2 fb_upsampled_flow(const float2 *__restrict__ p, int ph, int pw, int x, int y, int lh, int lw)
 {
     int x0, x1, y0, y1;
     float ax, ay;
-    lin_tap_f32(x, pw, lw, false, x0, x1, ax);
-    lin_tap_f32(y, ph, lh, true, y0, y1, ay);
+    if (lw == 2 * pw && lh == 2 * ph) {                              // every level of a frame whose sides divide by 8
+        up2_tap_f32(x, pw, false, x0, x1, ax);
+        up2_tap_f32(y, ph, true, y0, y1, ay);
+    } else {
+        lin_tap_f32(x, pw, lw, false, x0, x1, ax);
+        lin_tap_f32(y, ph, lh, true, y0, y1, ay);
+    }
     const float a0 = 1.f - ax, b0 = 1.f - ay;
     const float2 p00 = __ldg(p + (size_t)y0 * pw + x0), p01 = __ldg(p + (size_t)y0 * pw + x1);
     const float2 p10 = __ldg(p + (size_t)y1 * pw + x0), p11 = __ldg(p + (size_t)y1 * pw + x1);
@@ -532,6 +552,67 @@ k_fb_matrices_v4(const float *__restrict__ R, const float2 *__restrict__ flow, i
 #pragma unroll
     for (int c = 0; c < 5; c++)
         *reinterpret_cast<float4 *>(dst + c * FB_MS) = make_float4(m[0][c], m[1][c], m[2][c], m[3][c]);
+}
+
+// UpdateMatrices, "transposed gather" variant of k_fb_matrices_v4<0>.  ncu on v4: the 20 scalar R1
+// gathers per pixel are issued with the lanes of a warp 16 bytes apart (each lane owns 4 adjacent pixels),
+// so every gather instruction touches 16-20 sectors of which 4 bytes each are used -- 637 M sectors per
+// level-0 launch against 237 M for the one-pixel-per-lane kernel, L1 data pipe 88 % busy.  Here R0, flow
+// and M still move as 128-bit accesses (4 pixels per lane), but the per-pixel work runs with the lanes of
+// a warp on 32 ADJACENT pixels (4 rounds per 128-pixel row segment): the operands are transposed through
+// a per-warp shared-memory tile (conflict-free both ways), the gathers of a warp then fall into 1-2
+// cache lines, and the results go back through the same tile.  Arithmetic per pixel is fb_matrix_core,
+// unchanged, so M is bit-identical to v4's.  Requires w % 4 == 0.
+// INIT 0: flow read from memory; INIT 1: flow up-sampled on the fly from the coarser level (first
+// UpdateMatrices of a level), one pixel per lane like the gathers.
+template <int INIT>
+__global__ void __launch_bounds__(256)
+k_fb_matrices_t4(const float *__restrict__ R, const float2 *__restrict__ flow, int h, int w, float *__restrict__ M,
+                 const float2 *__restrict__ prev, int ph, int pw)
+{
+    __shared__ __align__(16) float tile[8][7 * 128];               // per warp: 5 planes of R0 | interleaved flow (256)
+    const int pair = blockIdx.z, lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    const int xw = blockIdx.x * 128, x = xw + lane * 4, y = blockIdx.y * 8 + wrp;
+    if (y >= h) return;                                              // warp-uniform
+    const bool have = x < w;
+    const size_t plane = (size_t)h * w, o = (size_t)y * w + x;
+    const float *R0 = R + (size_t)pair * 5 * plane, *R1 = R0 + 5 * plane;
+    float *t = tile[wrp];
+    if (have) {
+#pragma unroll
+        for (int c = 0; c < 5; c++)
+            *reinterpret_cast<float4 *>(t + c * 128 + lane * 4) = __ldg(reinterpret_cast<const float4 *>(R0 + c * plane + o));
+        if (INIT == 0) {
+            *reinterpret_cast<float4 *>(t + 640 + lane * 8) = __ldg(reinterpret_cast<const float4 *>(flow + (size_t)pair * plane + o));
+            *reinterpret_cast<float4 *>(t + 640 + lane * 8 + 4) = __ldg(reinterpret_cast<const float4 *>(flow + (size_t)pair * plane + o + 2));
+        }
+    }
+    __syncwarp();
+    float m[4][5];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int g = 32 * j + lane;                                 // pixel of this lane in round j
+        if (xw + g < w) {
+            const float2 f = INIT == 0 ? *reinterpret_cast<const float2 *>(t + 640 + 2 * g)
+                                       : fb_upsampled_flow(prev + (size_t)pair * ph * pw, ph, pw, xw + g, y, h, w);
+            fb_matrix_core(t[g], t[128 + g], t[256 + g], t[384 + g], t[512 + g], R1, plane, xw + g, y, h, w, f, m[j]);
+        } else {
+#pragma unroll
+            for (int c = 0; c < 5; c++) m[j][c] = 0.f;
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+#pragma unroll
+        for (int c = 0; c < 5; c++) t[c * 128 + 32 * j + lane] = m[j][c];
+    __syncwarp();
+    if (have) {
+        float *dst = M + (size_t)pair * fb_m_pair_floats(h, w) + fb_m_index((unsigned)(y * w + x));
+#pragma unroll
+        for (int c = 0; c < 5; c++)
+            *reinterpret_cast<float4 *>(dst + c * FB_MS) = *reinterpret_cast<const float4 *>(t + c * 128 + lane * 4);
+    }
 }
 
 constexpr int MS_W = 128, MS_OUT = 112, MS_R = 7, MS_H = 96, MS_SEG = 8;
@@ -853,8 +934,13 @@ int run_farneback(vqa_ctx *c, const uint8_t *gray, int npairs, int h, int w, dou
             else VQA_LAUNCH(c, k_fb_matrices<2>, gP, 256, 0, R, flow, lh, lw, M, prev, ph, pw);
         } else {
             VQA_BYTES(c, (60.0 * lw * lh + 8.0 * pw * ph) * npairs);
-            // the 4-pixel variant measured slower here (four serial bilinear up-samples per thread)
-            VQA_LAUNCH(c, k_fb_matrices<1>, gP, 256, 0, R, flow, lh, lw, M, prev, ph, pw);
+            // the 4-pixel variant measured slower here (four serial bilinear up-samples per thread); the
+            // transposed variant up-samples one pixel per lane (VQA_MAT_T4U, A/B knob read per call)
+            const char *t4u_env = getenv("VQA_MAT_T4U");
+            if (v4 && (t4u_env ? atoi(t4u_env) != 0 : false))
+                VQA_LAUNCH(c, k_fb_matrices_t4<1>, gV, 256, 0, R, flow, lh, lw, M, prev, ph, pw);
+            else
+                VQA_LAUNCH(c, k_fb_matrices<1>, gP, 256, 0, R, flow, lh, lw, M, prev, ph, pw);
         }
         // rows per block of the marching blur: long strips amortise the 15-row warm-up, but the small
         // pyramid levels need shorter strips to put >= ~3 waves of blocks on 148 SMs x 8 blocks
@@ -890,7 +976,11 @@ int run_farneback(vqa_ctx *c, const uint8_t *gray, int npairs, int h, int w, dou
                            last ? mag_sum : (double *)nullptr, (!last || flow_out) ? 1 : 0, (const float *)nullptr, (float *)nullptr);
             if (it < 2) {
                 VQA_BYTES(c, 68.0 * lw * lh * npairs);
-                if ((lw & 3) == 0 && mat_v4) {
+                const char *t4_env = getenv("VQA_MAT_T4");           // A/B knob, read per call
+                const bool mat_t4 = t4_env ? atoi(t4_env) != 0 : true;    // measured 3-5 % faster than v4<0>, same bits
+                if ((lw & 3) == 0 && mat_v4 && mat_t4) {
+                    VQA_LAUNCH(c, k_fb_matrices_t4<0>, dim3(cdiv(lw, 128), cdiv(lh, 8), npairs), 256, 0, R, flow, lh, lw, Mcur, prev, ph, pw);
+                } else if ((lw & 3) == 0 && mat_v4) {
                     VQA_LAUNCH(c, k_fb_matrices_v4<0>, dim3(cdiv(lw, 128), cdiv(lh, 8), npairs), 256, 0, R, flow, lh, lw, Mcur, prev, ph, pw);
                 } else {
                     VQA_LAUNCH(c, k_fb_matrices<0>, gP, 256, 0, R, flow, lh, lw, Mcur, prev, ph, pw);
