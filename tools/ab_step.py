@@ -18,6 +18,7 @@ SETS = {
               ("default again", {})],
     "mat_t4u": [("t4u=0", {"VQA_MAT_T4U": "0"}), ("t4u=1", {"VQA_MAT_T4U": "1"}), ("t4u=0 again", {"VQA_MAT_T4U": "0"}),
                 ("t4u=1 again", {"VQA_MAT_T4U": "1"}), ("all old", {"VQA_MAT_T4U": "0", "VQA_MAT_T4": "0"})],
+    "one": [("default", {}), ("default again", {})],
     "mat_t4": [("mat_t4=0", {"VQA_MAT_T4": "0"}), ("mat_t4=1", {"VQA_MAT_T4": "1"}), ("mat_t4=0 again", {"VQA_MAT_T4": "0"}),
                ("mat_t4=1 again", {"VQA_MAT_T4": "1"})],
 }
@@ -42,7 +43,7 @@ for name, env in VARIANTS:
     rep = ctx.kernel_report()
     ctx.kernel_profile(False)
     blur = sum(v["ms"] for k, v in rep.items() if "blur_solve" in k)
-    mat = {k: round(v["ms"], 3) for k, v in rep.items() if "matrices" in k}
+    mat = {k: round(v["ms"], 3) for k, v in rep.items() if "matrices" in k or (len(VARIANTS) <= 2 and v["ms"] > 0.25)}
     tot = sum(v["ms"] for v in rep.values())
     print(f"{name:14s} median {np.median(ts) * 1e3:8.2f} ms  min {min(ts) * 1e3:8.2f}  ({(F - 1) / np.median(ts):7.1f} frames/s)  "
           f"blur {blur:6.2f} ms  kernel-sum {tot:6.2f} ms  rows identical to default: {same}  {mat}", flush=True)
