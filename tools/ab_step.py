@@ -42,7 +42,7 @@ for name, env in VARIANTS:
     ctx.complexity_frames(clip, 1920, 1080)
     rep = ctx.kernel_report()
     ctx.kernel_profile(False)
-    blur = sum(v["ms"] for k, v in rep.items() if "blur_solve" in k)
+    blur = sum(v["ms"] for k, v in rep.items() if "blur_solve" in k and "EPI" not in k)
     mat = {k: round(v["ms"], 3) for k, v in rep.items() if "matrices" in k or (len(VARIANTS) <= 2 and v["ms"] > 0.25)}
     tot = sum(v["ms"] for v in rep.values())
     print(f"{name:14s} median {np.median(ts) * 1e3:8.2f} ms  min {min(ts) * 1e3:8.2f}  ({(F - 1) / np.median(ts):7.1f} frames/s)  "
