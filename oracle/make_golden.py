@@ -173,11 +173,13 @@ def main_orb():
     frames += [("mid", i, cv2.cvtColor(mid[i], cv2.COLOR_BGR2GRAY)) for i in (0, 4)]
     frames += [("hd", 1, cv2.cvtColor(hd[1], cv2.COLOR_BGR2GRAY))]
     frames += [("noise_200x333_seed21", 0, noise)]
+    uhd = S.synth_clip(1, 2160, 3840, seed=2)                    # BASELINE.json config 4 frame size
+    frames += [("uhd", 0, cv2.cvtColor(uhd[0], cv2.COLOR_BGR2GRAY))]
     # resize -> gray order of the orb_size knob: gray(resize(frame, (w, h))), INTER_LINEAR
     frames += [("hd_resized_640x360", 1, cv2.cvtColor(cv2.resize(hd[1], (640, 360)), cv2.COLOR_BGR2GRAY))]
     for name, idx, gray in frames:
         for cname, cfg in ORB_CONFIGS.items():
-            if name == "hd" and cname not in ("default", "n1000"):
+            if (name == "hd" and cname not in ("default", "n1000")) or (name == "uhd" and cname != "default"):
                 continue
             g["cases"].append(dict(clip=name, frame=idx, shape=list(gray.shape), gray_sha=sha(gray), cfg=cname,
                                    **orb_general(gray, **cfg)))

@@ -37,6 +37,8 @@ def golden_gray(case, small_clip, synth, cache={}):
             g = NO.bgr2gray(synth.synth_clip(5, 270, 480, seed=3)[i])
         elif name == "hd":
             g = NO.bgr2gray(synth.synth_clip(3, 1080, 1920, seed=0)[i])
+        elif name == "uhd":
+            g = NO.bgr2gray(synth.synth_clip(1, 2160, 3840, seed=2)[i])
         elif name == "hd_resized_640x360":
             g = NO.bgr2gray(NO.resize_linear_u8(synth.synth_clip(3, 1080, 1920, seed=0)[i], 640, 360))
         else:
@@ -59,14 +61,14 @@ def digest_keypoints(rows):
 
 
 def test_orb_oracle_matches_cv2_fixtures(orb_golden, small_clip, synth):
-    assert len(orb_golden["cases"]) >= 37
+    assert len(orb_golden["cases"]) >= 38
     for case in orb_golden["cases"]:
         gray = golden_gray(case, small_clip, synth)
         rows, per = OO.orb_detect(gray, **CFGS[case["cfg"]])
         assert per == case["per_level"], (case["clip"], case["frame"], case["cfg"])
         assert len(rows) == case["count"]
         assert digest(rows) == case["digest"], "Harris responses are not bit-identical to cv2's"
-        if case["clip"] != "hd":                  # every cv2.KeyPoint field incl. the orientation (pure-Python loops: skip 1080p)
+        if case["clip"] not in ("hd", "uhd"):     # every cv2.KeyPoint field incl. the orientation (pure-Python loops: skip 1080p / 4K)
             assert digest_keypoints(OO.orb_keypoints(gray, **CFGS[case["cfg"]])) == case["digest_keypoints"], \
                 (case["clip"], case["frame"], case["cfg"])
 
