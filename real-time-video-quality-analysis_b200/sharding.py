@@ -160,6 +160,8 @@ def plan_clip_shards(clip_frames, world: int):
     if n >= world:
         load = [0] * world
         for c in sorted(range(n), key=lambda i: (-clip_frames[i], i)):
+            if clip_frames[c] <= 0:                       # an empty clip has nothing to shard
+                continue
             r = min(range(world), key=lambda j: (load[j], j))
             plan[r].append((c, 0, int(clip_frames[c])))
             load[r] += int(clip_frames[c])
