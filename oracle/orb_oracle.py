@@ -203,28 +203,32 @@ def _reflect101(i: int, n: int) -> int:
     return i
 
 
-def ic_angle(img: np.ndarray, x: int, y: int, umax=None) -> np.float32:
-    """orb.cpp ICAngles: intensity-centroid orientation over the circular patch of radius 15; pixels
-    outside the level image come from its BORDER_REFLECT_101 extension (only reachable when
-    edgeThreshold < 16)."""
+_PATCH_CACHE = {}
+
+
+def _patch_weights(umax):
+    """(U * mask, V * mask) of the circular patch: mask[v, u] = |u| <= umax[|v|]."""
+    key = tuple(umax)
+    if key not in _PATCH_CACHE:
+        half = len(umax) - 1
+        v, u = np.mgrid[-half:half + 1, -half:half + 1]
+        mask = np.abs(u) <= np.asarray(umax)[np.abs(v)]
+        _PATCH_CACHE[key] = ((u * mask).astype(np.int64), (v * mask).astype(np.int64))
+    return _PATCH_CACHE[key]
+
+
+def ic_angle(img: np.ndarray, x: int, y: int, umax=None, padded=None) -> np.float32:
+    """orb.cpp ICAngles: intensity-centroid orientation over the circular patch of radius 15
+    (m10 = sum u*I, m01 = sum v*I, integers); pixels outside the level image come from its
+    BORDER_REFLECT_101 extension (only reachable when edgeThreshold < 16).  ``padded`` = the level
+    reflect-padded by the patch radius (pass it when calling for many keypoints)."""
     umax = umax or umax_table()
-    h, w = img.shape
     half = len(umax) - 1
-
-    def P(yy, xx):
-        return int(img[_reflect101(yy, h), _reflect101(xx, w)])
-
-    m01 = m10 = 0
-    for u in range(-half, half + 1):
-        m10 += u * P(y, x + u)
-    for v in range(1, half + 1):
-        d, vs = umax[v], 0
-        for u in range(-d, d + 1):
-            vp, vm = P(y + v, x + u), P(y - v, x + u)
-            vs += vp - vm
-            m10 += u * (vp + vm)
-        m01 += v * vs
-    return fast_atan2(_F(m01), _F(m10))
+    if padded is None:
+        padded = np.pad(img, half, mode="reflect")
+    wu, wv = _patch_weights(umax)
+    patch = padded[y:y + 2 * half + 1, x:x + 2 * half + 1].astype(np.int64)
+    return fast_atan2(_F(int((patch * wv).sum())), _F(int((patch * wu).sum())))
 
 
 def orb_keypoints(gray: np.ndarray, **kw):
@@ -233,10 +237,14 @@ def orb_keypoints(gray: np.ndarray, **kw):
     nlevels, sf = kw.get("nlevels", NLEVELS), kw.get("scale_factor", SCALE_FACTOR)
     rows, _ = orb_detect(gray, **kw)
     pyr, scales, um = pyramid(gray, nlevels, sf), level_scales(nlevels, sf), umax_table()
+    padded = {}
     out = []
     for l, x, y, r, _s in rows:
         sc = scales[l]
-        out.append((l, float(_F(x) * sc), float(_F(y) * sc), float(_F(PATCH_SIZE) * sc), float(ic_angle(pyr[l], x, y, um)), r))
+        if l not in padded:
+            padded[l] = np.pad(pyr[l], HALF_PATCH, mode="reflect")
+        out.append((l, float(_F(x) * sc), float(_F(y) * sc), float(_F(PATCH_SIZE) * sc),
+                    float(ic_angle(pyr[l], x, y, um, padded[l])), r))
     return out
 
 

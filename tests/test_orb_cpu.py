@@ -68,9 +68,9 @@ def test_orb_oracle_matches_cv2_fixtures(orb_golden, small_clip, synth):
         assert per == case["per_level"], (case["clip"], case["frame"], case["cfg"])
         assert len(rows) == case["count"]
         assert digest(rows) == case["digest"], "Harris responses are not bit-identical to cv2's"
-        if case["clip"] not in ("hd", "uhd"):     # every cv2.KeyPoint field incl. the orientation (pure-Python loops: skip 1080p / 4K)
-            assert digest_keypoints(OO.orb_keypoints(gray, **CFGS[case["cfg"]])) == case["digest_keypoints"], \
-                (case["clip"], case["frame"], case["cfg"])
+        # every cv2.KeyPoint field incl. the orientation
+        assert digest_keypoints(OO.orb_keypoints(gray, **CFGS[case["cfg"]])) == case["digest_keypoints"], \
+            (case["clip"], case["frame"], case["cfg"])
 
 
 def test_orb_at_64x64_is_the_reference_path(small_clip):
