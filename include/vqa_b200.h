@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define VQA_ABI_VERSION 2
+#define VQA_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define VQA_API __attribute__((visibility("default")))
@@ -170,6 +170,23 @@ VQA_API int vqa_analyze_clip(vqa_ctx *ctx, const uint8_t *bgr, int n, int h, int
                              const int32_t plane_w[3], const int32_t plane_h[3], const int32_t stride[3],
                              int n_pairs, vqa_fr_metrics *fr_out);
 
+/* ---- f4: both halves of one clip from ONE upload of yuv420p planes ----------------------------------
+ * The reference scores the source against its encode (run_ffmpeg_metrics(input, encoded),
+ * video_processing.py:216) and then analyses the ENCODED file (calculate_average_scene_complexity,
+ * video_processing.py:242), whose BGR frames are what cv2.VideoCapture.read (complexity_metrics.py:38-111)
+ * makes of the encode's yuv420p planes: libswscale's unscaled yuv420p -> bgr24 converter.  That conversion
+ * is reproduced bit-exactly on the device, so the planes are uploaded once (3 bytes per pixel and frame pair
+ * instead of 6) and feed both PSNR/SSIM and the seven complexity metrics.
+ *   main_planes  Y, U, V stacks of the encoded clip ([0:v] of the filter graphs); n frames of h x w (both
+ *                even); plane p of frame i at main_planes[p] + i * plane_h[p] * stride[p]
+ *   ref_planes   the source clip's stacks ([1:v]) or NULL: complexity rows only, fr_out untouched
+ *   halo_planes  optional Y, U, V of the previous sampled frame of the encoded clip (frame-range sharding)
+ *   on_device    planes (all of them) are device pointers on the context's GPU
+ */
+VQA_API int vqa_analyze_clip_yuv420(vqa_ctx *ctx, const uint8_t *const main_planes[3], const uint8_t *const ref_planes[3],
+                                    const int32_t stride[3], int n, int h, int w, const uint8_t *const halo_planes[3],
+                                    int on_device, const vqa_cfg *cfg, vqa_frame_metrics *rows_out, vqa_fr_metrics *fr_out);
+
 /* ---- a9/a10: framerate variation + EWM-smoothed mean ----------------------------------------
  * vqa_framerate_series: process_frame_interval_for_parallel over consecutive timestamps
  * (complexity_metrics.py:150-165, driven at :296-298): fps[k] = 1000/(t[k+1]-t[k]) or 0.
@@ -181,6 +198,27 @@ VQA_API int vqa_analyze_clip(vqa_ctx *ctx, const uint8_t *bgr, int n, int h, int
 VQA_API int vqa_framerate_series(vqa_ctx *ctx, const double *timestamps_ms, int n, double *fps_out /* n-1 */);
 VQA_API int vqa_ewm_partial(vqa_ctx *ctx, const double *x, int n_local, int64_t offset, int64_t total,
                     double alpha, double *partial_out);
+
+/* ---- e: multi-GPU close of a clip (frame-range / clip sharding, SURVEY.md 8 e) -----------------------
+ * One process per GPU.  Each rank analyses its frame range (vqa_complexity_frames / vqa_analyze_clip_yuv420
+ * with the previous rank's last frame as halo), forms per-clip partial weighted sums with vqa_ewm_partial,
+ * and vqa_clip_reduce sums them over all ranks: one fused buffer [n_f64 doubles | n_i64 integers], ONE
+ * ncclAllReduce(sum) on the context's stream, results in place on every rank.  This stands where the
+ * reference gathers the per-frame lists of its process pool (complexity_metrics.py:128-148) and takes
+ * np.mean at :301-310.  Integers are carried exactly (the call fails rather than round above 2^53).
+ *   nccl_comm   an ncclComm_t the caller owns whose rank's device is the context's GPU, or NULL to use
+ *               the communicator created by vqa_comm_init
+ * vqa_comm_unique_id (rank 0; host-only) + vqa_comm_init (every rank, with the id rank 0 distributed
+ * out of band) wrap ncclGetUniqueId / ncclCommInitRank for hosts without an NCCL binding of their own.
+ * vqa_comm_halo_exchange: rank r sends `send` (its last frame, device memory) to r+1 and receives
+ * rank r-1's into `recv` over NVLink; NULL on the open ends.  NCCL is dlopen'ed on first use.
+ */
+#define VQA_COMM_ID_BYTES 128
+VQA_API int vqa_comm_unique_id(uint8_t *id_out /* VQA_COMM_ID_BYTES */);
+VQA_API int vqa_comm_init(vqa_ctx *ctx, const uint8_t *id /* VQA_COMM_ID_BYTES */, int rank, int world);
+VQA_API int vqa_comm_destroy(vqa_ctx *ctx);
+VQA_API int vqa_clip_reduce(vqa_ctx *ctx, void *nccl_comm, double *partials, int n_f64, int64_t *ints, int n_i64);
+VQA_API int vqa_comm_halo_exchange(vqa_ctx *ctx, void *nccl_comm, const uint8_t *send, uint8_t *recv, size_t bytes);
 
 /* ---- debug / stage-level parity taps (tests only; device work, host results) ------------ */
 VQA_API int vqa_debug_gray(vqa_ctx *ctx, const uint8_t *bgr, int h, int w, uint8_t *gray_out);
@@ -196,6 +234,9 @@ VQA_API int vqa_debug_orb_pyramid(vqa_ctx *ctx, const uint8_t *gray, int h, int 
 /* host-only: packed (offset << 16 | weight of the right tap, 8.8 fixed point) taps of INTER_LINEAR_EXACT */
 VQA_API int vqa_debug_exact_taps(int src_len, int dst_len, uint32_t *taps_out);
 VQA_API int vqa_debug_dct(vqa_ctx *ctx, const uint8_t *gray, int h, int w, int impl, float *coef_out /* h*w */);
+/* the yuv420p -> BGR conversion of vqa_analyze_clip_yuv420 on one frame (h, w even; dense planes) */
+VQA_API int vqa_debug_yuv2bgr(vqa_ctx *ctx, const uint8_t *y, const uint8_t *u, const uint8_t *v, int h, int w,
+                              uint8_t *bgr_out /* h*w*3 */);
 
 #ifdef __cplusplus
 }

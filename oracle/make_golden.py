@@ -206,9 +206,80 @@ def main_fr():
     print("wrote psnr_cv2.json:", len(g["cases"]), "cases")
 
 
+def write_y4m(path, Y, U, V):
+    """Minimal yuv4mpeg2 writer (yuv420p): the one container cv2's bundled libavformat demuxes that carries
+    raw planes, so cv2.VideoCapture.read() returns exactly swscale(yuv420p -> bgr24) of the planes given."""
+    with open(path, "wb") as f:
+        f.write(b"YUV4MPEG2 W%d H%d F30:1 Ip A1:1 C420jpeg\n" % (Y.shape[2], Y.shape[1]))
+        for i in range(len(Y)):
+            f.write(b"FRAME\n")
+            f.write(Y[i].tobytes())
+            f.write(U[i].tobytes())
+            f.write(V[i].tobytes())
+
+
+def read_video(path):
+    import cv2
+    cap = cv2.VideoCapture(path)
+    out = []
+    while True:
+        ok, a = cap.read()
+        if not ok:
+            break
+        out.append(a)
+    cap.release()
+    return np.stack(out)
+
+
+def exhaustive_yuv_frame():
+    """One 4096x4096 yuv420p frame in which every (Y,U,V) triple occurs exactly once."""
+    cidx = np.arange(2048 * 2048).reshape(2048, 2048)
+    U = ((cidx >> 6) & 255).astype(np.uint8)
+    V = ((cidx >> 14) & 255).astype(np.uint8)
+    s = cidx & 63
+    Y = np.zeros((4096, 4096), np.uint8)
+    Y[0::2, 0::2] = (4 * s).astype(np.uint8)
+    Y[0::2, 1::2] = (4 * s + 1).astype(np.uint8)
+    Y[1::2, 0::2] = (4 * s + 2).astype(np.uint8)
+    Y[1::2, 1::2] = (4 * s + 3).astype(np.uint8)
+    return Y, U, V
+
+
+def main_yuv2bgr():
+    """tests/golden/yuv2bgr_cv2.{json,npz}: BGR frames cv2.VideoCapture decodes from yuv4mpeg files whose planes
+    we chose: (1) sha256 of the decode of the exhaustive frame (all 2^24 triples), (2) sha256 of
+    decodes of random planes at even sizes from 2x2 to 1080p, (3) one small random case stored in full."""
+    import tempfile
+    import cv2
+    g = dict(meta=dict(cv2=cv2.__version__, source="cv2.VideoCapture(<yuv4mpeg2 C420jpeg file>).read()",
+                       note="odd frame sizes take another swscale path and are not covered"), cases=[])
+    tmp = tempfile.mkdtemp()
+    path = os.path.join(tmp, "t.y4m")
+    Y, U, V = exhaustive_yuv_frame()
+    write_y4m(path, Y[None], U[None], V[None])
+    g["exhaustive_sha"] = sha(read_video(path)[0])
+    rng = np.random.default_rng(2024)
+    for (h, w) in ((2, 2), (4, 6), (16, 8), (18, 10), (50, 34), (98, 102), (144, 192), (146, 198), (270, 482), (1080, 1920)):
+        n = 2 if h < 1000 else 1
+        Yr = rng.integers(0, 256, (n, h, w), dtype=np.uint8)
+        Ur = rng.integers(0, 256, (n, h // 2, w // 2), dtype=np.uint8)
+        Vr = rng.integers(0, 256, (n, h // 2, w // 2), dtype=np.uint8)
+        write_y4m(path, Yr, Ur, Vr)
+        got = read_video(path)
+        assert got.shape == (n, h, w, 3)
+        g["cases"].append(dict(h=h, w=w, n=n, seed=2024, y_sha=sha(Yr), u_sha=sha(Ur), v_sha=sha(Vr), bgr_sha=sha(got)))
+        if (h, w) == (146, 198):
+            np.savez_compressed(os.path.join(GOLD, "yuv2bgr_cv2.npz"), y=Yr, u=Ur, v=Vr, bgr=got)
+    with open(os.path.join(GOLD, "yuv2bgr_cv2.json"), "w") as f:
+        json.dump(g, f, indent=1)
+    print("wrote yuv2bgr_cv2.json:", len(g["cases"]), "cases, exhaustive sha", g["exhaustive_sha"][:16])
+
+
 if __name__ == "__main__":
     if "--fr" in sys.argv:
         main_fr()
+    elif "--yuv2bgr" in sys.argv:
+        main_yuv2bgr()
     elif "--orb" in sys.argv:
         main_orb()
     else:

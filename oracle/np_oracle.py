@@ -250,3 +250,56 @@ def ssim_frame(main_planes, ref_planes):
     tot = float(sum(areas))
     s = [ssim_plane(m, r) for m, r in zip(main_planes, ref_planes)]
     return dict(ssim=s, ssim_all=sum(v * (a / tot) for v, a in zip(s, areas)))
+
+
+def ssim_plane_textbook(a, b) -> float:
+    """Independent float64 evaluation of the structural-similarity index (Wang et al. 2004) on vf_ssim.c's
+    window set: uniform 8x8 windows on a 4-pixel grid, L = 255, K2 = 0.03 with sample (n-1 = 63) variances.
+    Dividing vf_ssim.c's integer expression by 64^2 (mean term) and 64*63 (variance term) gives exactly
+        (2 mu_p mu_q + C1) (2 cov + C2) / ((mu_p^2 + mu_q^2 + C1) (var_p + var_q + C2))
+    with C2 = (0.03*255)^2 and C1 = (0.01*255)^2 / 64 (ssim_c1 = .01^2 255^2 64 is added to sums that carry a
+    factor 64^2 -- x264's constant, kept by FFmpeg), both rounded to integers in the scaled domain.  This
+    function shares no code with ssim_plane / the C oracle: it works on pixel windows in floating point, so
+    agreement (~1e-6) checks the block sums, the window set and the plane mean; it is a known-answer pin on
+    the published definition, not on an FFmpeg binary (none exists in the image or on the GPU box)."""
+    a = a.astype(np.float64)
+    b = b.astype(np.float64)
+    h, w = a.shape
+    c1, c2 = 416.0 / 4096.0, 235963.0 / (64.0 * 63.0)
+    vals = []
+    for y in range(0, (h >> 2) * 4 - 7, 4):
+        for x in range(0, (w >> 2) * 4 - 7, 4):
+            p, q = a[y:y + 8, x:x + 8], b[y:y + 8, x:x + 8]
+            mp, mq = p.mean(), q.mean()
+            vp, vq = p.var(ddof=1), q.var(ddof=1)
+            cov = ((p - mp) * (q - mq)).sum() / 63.0
+            vals.append((2 * mp * mq + c1) * (2 * cov + c2) / ((mp * mp + mq * mq + c1) * (vp + vq + c2)))
+    return float(np.mean(vals))
+
+
+# --------------------------------------------------------------------------- f4: yuv420p -> BGR
+
+
+def yuv420_to_bgr(y, u, v) -> np.ndarray:
+    """cv2.VideoCapture.read() of a yuv420p stream (complexity_metrics.py:38-111 on the ENCODED file,
+    video_processing.py:242): libswscale's unscaled yuv420p -> bgr24 converter (x86 SIMD path, taken for every
+    even frame size), nearest chroma, 16-bit fixed point with arithmetic shifts:
+        yy = ((Y << 3) - 128) * 9539 >> 16 ;  uu = (U << 3) - 1024 ;  vv = (V << 3) - 1024
+        B = sat8(yy + (uu * 16525 >> 16)) ; G = sat8(yy + (uu * -3209 >> 16) + (vv * -6660 >> 16)) ;
+        R = sat8(yy + (vv * 13075 >> 16))
+    Pinned on cv2 itself (yuv4mpeg files through cv2.VideoCapture): all 2^24 (Y,U,V) triples and even sizes
+    from 2x2 to 1080p -- oracle/make_golden.py --yuv2bgr, tests/golden/yuv2bgr_cv2.{json,npz}.
+    y: [h,w]; u, v: [h/2,w/2] uint8 (or stacks with a leading frame axis).  Returns [...,h,w,3] uint8."""
+    y = np.asarray(y)
+    h, w = y.shape[-2:]
+    if (h | w) & 1:
+        raise ValueError("yuv420p -> BGR is defined here for even frame sizes only")
+    uf = np.repeat(np.repeat(np.asarray(u), 2, axis=-2), 2, axis=-1).astype(np.int64)
+    vf = np.repeat(np.repeat(np.asarray(v), 2, axis=-2), 2, axis=-1).astype(np.int64)
+    yy = (((y.astype(np.int64) << 3) - 128) * 9539) >> 16
+    uu = (uf << 3) - 1024
+    vv = (vf << 3) - 1024
+    b = yy + ((uu * 16525) >> 16)
+    g = yy + ((uu * -3209) >> 16) + ((vv * -6660) >> 16)
+    r = yy + ((vv * 13075) >> 16)
+    return np.clip(np.stack([b, g, r], axis=-1), 0, 255).astype(np.uint8)

@@ -24,8 +24,11 @@ EXPORTS = [
     "vqa_psnr_ssim_planar", "vqa_analyze_clip", "vqa_framerate_series", "vqa_ewm_partial", "vqa_debug_gray",
     "vqa_debug_resize", "vqa_debug_hist", "vqa_debug_orb", "vqa_kernel_profile", "vqa_kernel_report", "vqa_debug_canny", "vqa_debug_flow", "vqa_debug_dct",
     "vqa_orb_default_cfg", "vqa_orb_describe", "vqa_orb_detect", "vqa_debug_orb_pyramid", "vqa_debug_exact_taps",
+    "vqa_analyze_clip_yuv420", "vqa_debug_yuv2bgr",
+    "vqa_comm_unique_id", "vqa_comm_init", "vqa_comm_destroy", "vqa_clip_reduce", "vqa_comm_halo_exchange",
 ]
-ABI_VERSION = 2
+COMM_ID_BYTES = 128
+ABI_VERSION = 3
 
 
 class VqaError(RuntimeError):
@@ -93,6 +96,14 @@ def load_library():
         L.vqa_psnr_ssim_planar.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), i32p, i32p, i32p, C.c_int, C.c_int, vp]
         L.vqa_analyze_clip.argtypes = [vp, u8p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.POINTER(Cfg), vp,
                                        C.POINTER(vp), C.POINTER(vp), i32p, i32p, i32p, C.c_int, vp]
+        L.vqa_analyze_clip_yuv420.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), i32p, C.c_int, C.c_int, C.c_int,
+                                              C.POINTER(vp), C.c_int, C.POINTER(Cfg), vp, vp]
+        L.vqa_debug_yuv2bgr.argtypes = [vp, u8p, u8p, u8p, C.c_int, C.c_int, u8p]
+        L.vqa_comm_unique_id.argtypes = [vp]
+        L.vqa_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
+        L.vqa_comm_destroy.argtypes = [vp]
+        L.vqa_clip_reduce.argtypes = [vp, vp, vp, C.c_int, vp, C.c_int]
+        L.vqa_comm_halo_exchange.argtypes = [vp, vp, vp, vp, C.c_size_t]
         L.vqa_framerate_series.argtypes = [vp, vp, C.c_int, vp]
         L.vqa_ewm_partial.argtypes = [vp, vp, C.c_int, C.c_int64, C.c_int64, C.c_double, f64p]
         L.vqa_debug_gray.argtypes = [vp, u8p, C.c_int, C.c_int, u8p]
@@ -345,6 +356,103 @@ class Context:
         del keep
         return rows, fr
 
+    def analyze_clip_yuv420(self, main_planes, ref_planes, resize_width, resize_height, mask=M_ALL, halo_planes=None,
+                            dct_impl=0, orb_size=None):
+        """Both halves of a clip from ONE set of yuv420p planes (vqa_analyze_clip_yuv420).
+        main_planes = (Y [n,h,w], U [n,h/2,w/2], V [n,h/2,w/2]) of the ENCODED clip; the complexity metrics run
+        on the BGR frames cv2.VideoCapture would decode from them (bit-exact libswscale conversion on the
+        device).  ref_planes = the source clip's planes for PSNR/SSIM, or None.  numpy arrays (host) or CUDA
+        tensors (all of them).  halo_planes = (Y [h,w], U, V) of the previous sampled frame, or None.
+        Returns (rows, fr) -- fr is None without ref_planes."""
+        on_dev = int(_is_torch_tensor(main_planes[0]) and main_planes[0].is_cuda)
+        keep = []
+
+        def ptrs(planes, frame_dims):
+            arr, shapes = (C.c_void_p * 3)(), []
+            for i in range(3):
+                a = planes[i]
+                if on_dev:
+                    if not (_is_torch_tensor(a) and a.is_cuda and a.device.index == self.device):
+                        raise TypeError("all planes must be CUDA tensors on the context's device")
+                    a = a.contiguous()
+                    if str(a.dtype) != "torch.uint8":
+                        raise TypeError("planes must be uint8")
+                    arr[i] = a.data_ptr()
+                else:
+                    a = _np_u8(a)
+                    arr[i] = a.ctypes.data
+                if len(a.shape) != frame_dims:
+                    raise TypeError("planes must be [n,h_c,w_c] stacks (halo: [h_c,w_c])")
+                shapes.append(tuple(int(v) for v in a.shape))
+                keep.append(a)
+            return arr, shapes
+
+        mp, shp = ptrs(main_planes, 3)
+        n, h, w = shp[0]
+        if (h | w) & 1:
+            raise VqaError("yuv420p frames must have even sizes")
+        if shp[1] != (n, h // 2, w // 2) or shp[2] != (n, h // 2, w // 2):
+            raise TypeError("U/V planes must be [n,h/2,w/2]")
+        rp = None
+        if ref_planes is not None:
+            rp, rshp = ptrs(ref_planes, 3)
+            if rshp != shp:
+                raise TypeError("main/ref plane shapes differ")
+        hp = None
+        if halo_planes is not None:
+            hp, hshp = ptrs(halo_planes, 2)
+            if hshp != [(h, w), (h // 2, w // 2), (h // 2, w // 2)]:
+                raise TypeError("halo planes must match the frame size")
+        if on_dev:
+            import torch
+            torch.cuda.current_stream(self.device).synchronize()
+        st = (C.c_int32 * 3)(w, w // 2, w // 2)
+        rows = np.zeros(n, dtype=FRAME_DTYPE)
+        fr = np.zeros(n, dtype=FR_DTYPE) if rp is not None else None
+        ow, oh = (int(orb_size[0]), int(orb_size[1])) if orb_size else (0, 0)
+        cfg = Cfg(int(resize_width), int(resize_height), int(mask), int(dct_impl), ow, oh)
+        with self.lock:
+            rc = self.lib.vqa_analyze_clip_yuv420(self.h, mp, rp, st, n, h, w, hp, on_dev, C.byref(cfg),
+                                                  C.c_void_p(rows.ctypes.data),
+                                                  C.c_void_p(fr.ctypes.data) if fr is not None else None)
+        self._check(rc, "vqa_analyze_clip_yuv420")
+        del keep
+        return rows, fr
+
+    # ------------------------------------------------------------------ e: multi-GPU close (NCCL inside the library)
+    def comm_init(self, rank: int, world: int, id_bytes: bytes):
+        """Create the context's own NCCL communicator (vqa_comm_init); ``id_bytes`` from comm_unique_id() of
+        rank 0, distributed by the caller (e.g. torch.distributed.broadcast_object_list, a file, MPI)."""
+        if len(id_bytes) != COMM_ID_BYTES:
+            raise ValueError("NCCL unique id must be %d bytes" % COMM_ID_BYTES)
+        buf = C.create_string_buffer(bytes(id_bytes), COMM_ID_BYTES)
+        with self.lock:
+            self._check(self.lib.vqa_comm_init(self.h, buf, int(rank), int(world)), "vqa_comm_init")
+        self.comm_rank, self.comm_world = int(rank), int(world)
+
+    def comm_destroy(self):
+        with self.lock:
+            self._check(self.lib.vqa_comm_destroy(self.h), "vqa_comm_destroy")
+        self.comm_world = 0
+
+    def clip_reduce(self, partials, ints):
+        """Sum over all ranks (ONE ncclAllReduce on the context's stream): float64 partials and int64 totals."""
+        p = np.ascontiguousarray(partials, dtype=np.float64).copy()
+        i = np.ascontiguousarray(ints, dtype=np.int64).copy()
+        with self.lock:
+            rc = self.lib.vqa_clip_reduce(self.h, None, C.c_void_p(p.ctypes.data) if p.size else None, int(p.size),
+                                          C.c_void_p(i.ctypes.data) if i.size else None, int(i.size))
+        self._check(rc, "vqa_clip_reduce")
+        return p.reshape(np.shape(partials)), i.reshape(np.shape(ints))
+
+    def halo_exchange(self, send, recv):
+        """send: CUDA uint8 tensor (this rank's last frame) or None; recv: CUDA uint8 tensor or None."""
+        nbytes = int((send if send is not None else recv).numel())
+        with self.lock:
+            rc = self.lib.vqa_comm_halo_exchange(self.h, None, C.c_void_p(send.data_ptr()) if send is not None else None,
+                                                 C.c_void_p(recv.data_ptr()) if recv is not None else None, nbytes)
+        self._check(rc, "vqa_comm_halo_exchange")
+
     # ------------------------------------------------------------------ a9 / a10
     def framerate_series(self, timestamps_ms):
         ts = np.ascontiguousarray(timestamps_ms, dtype=np.float64)
@@ -404,6 +512,16 @@ class Context:
             out[name] = dict(launches=int(n), ms=float(ms), bytes=float(b), flops=float(fl))
         return out
 
+    def debug_yuv2bgr(self, y, u, v):
+        y, u, v = _np_u8(y), _np_u8(u), _np_u8(v)
+        h, w = y.shape
+        if u.shape != (h // 2, w // 2) or v.shape != u.shape:
+            raise TypeError("U/V planes must be [h/2,w/2]")
+        out = np.empty((h, w, 3), np.uint8)
+        self._check(self.lib.vqa_debug_yuv2bgr(self.h, y.ctypes.data, u.ctypes.data, v.ctypes.data, h, w, out.ctypes.data),
+                    "debug_yuv2bgr")
+        return out
+
     def debug_canny(self, gray):
         g = _np_u8(gray)
         out = np.empty_like(g)
@@ -421,6 +539,16 @@ class Context:
         out = np.empty(g.shape, np.float32)
         self._check(self.lib.vqa_debug_dct(self.h, g.ctypes.data, g.shape[0], g.shape[1], impl, out.ctypes.data), "debug_dct")
         return out
+
+
+def comm_unique_id() -> bytes:
+    """ncclGetUniqueId through the library (rank 0 calls it and distributes the 128 bytes)."""
+    L = load_library()
+    buf = C.create_string_buffer(COMM_ID_BYTES)
+    rc = L.vqa_comm_unique_id(buf)
+    if rc != 0:
+        raise VqaError(f"vqa_comm_unique_id failed ({rc}): {L.vqa_last_error(None).decode()}")
+    return buf.raw
 
 
 def orb_describe(h: int, w: int, cfg: OrbCfg | None = None):

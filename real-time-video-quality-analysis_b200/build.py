@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 SO = os.path.join(HERE, "libvqa_b200.so")
 SOURCES = ["api.cu", "ingest.cu", "canny.cu", "fast_orb.cu", "orb.cu", "dct.cu", "dct_umma.cu", "farneback.cu",
-           "psnr_ssim.cu", "stats.cu"]
+           "psnr_ssim.cu", "yuv.cu", "stats.cu", "comm.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr"]
 

@@ -142,7 +142,13 @@ int vqa_init(int device, vqa_ctx **out)
         return set_err(nullptr, VQA_E_CUDA, "stream creation failed");
     }
     c->own_stream = true;
+    // (the library reads no environment variables unless it is built with -DVQA_AB: the A/B knobs of the
+    // measurement notes are compile-time options of the development build, not of the product)
+#ifdef VQA_AB
     const unsigned wait_flag = (getenv("VQA_SPIN_WAIT") && atoi(getenv("VQA_SPIN_WAIT"))) ? 0u : (unsigned)cudaEventBlockingSync;
+#else
+    const unsigned wait_flag = (unsigned)cudaEventBlockingSync;
+#endif
     for (int i = 0; i < 3; i++) {
         cudaEventCreateWithFlags(&c->ev_copy[i], cudaEventDisableTiming);
         // host waits on these must yield, not spin: a spinning waiter in a second thread (the FR half)
@@ -161,6 +167,7 @@ void vqa_destroy(vqa_ctx *c)
     cudaStreamSynchronize(c->stream);
     cudaStreamSynchronize(c->copy_stream);
     cudaStreamSynchronize(c->side_stream);
+    comm_release(c);
     dct_umma_release(c);
     orb_release(c);
     for (auto &kv : c->bufs) if (kv.second.p) cudaFree(kv.second.p);
@@ -259,13 +266,16 @@ int vqa_stage_ms(vqa_ctx *c, const char *stage, double *ms, uint64_t *launches)
 }
 
 // ------------------------------------------------------------------------------------------
-static int pick_chunk(vqa_ctx *c, int h, int w, int rw, int rh, unsigned mask, int ow = 0, int oh = 0)
+static int pick_chunk(vqa_ctx *c, int h, int w, int rw, int rh, unsigned mask, int ow = 0, int oh = 0, bool yuv = false)
 {
+#ifdef VQA_AB
     const char *env = getenv("VQA_CHUNK");
     if (env && atoi(env) > 0) return atoi(env);
+#endif
     const size_t free_b = free_device_memory(c);
     const double hw = (double)h * w, rr = (double)rw * rh;
-    double per = hw * 3 * 3 + hw * 2 + rr * 8;                         // input double buffer, gray, labels/state
+    double per = hw * 3 * 3 + hw * 2 + rr * 8;                         // input staging slots, gray, labels/state
+    if (yuv) per += hw * 3;                                            // BGR frames derived from the yuv420p planes
     if (mask & VQA_M_MOTION) per += hw * 66;                           // I, R, M, 2 x flow
     if (mask & (VQA_M_DCT | VQA_M_TDCT)) per += rr * 16;               // X, T (hi/lo), C
     if ((mask & VQA_M_ORB) && ow > 0 && !(ow == 64 && oh == 64)) per += (double)ow * oh * 17;   // bgr+gray, pyramid, 3 lists
@@ -308,16 +318,29 @@ int side_issue(vqa_ctx *c, SideLoad *s, size_t budget)
     return VQA_OK;
 }
 
+// yuv420p input (vqa_analyze_clip_yuv420): the planes of the ENCODED clip (`main`) are converted to BGR on the
+// device chunk by chunk (yuv.cu) and feed the complexity metrics; with `ref` planes the same upload also
+// feeds PSNR/SSIM.  Dense stacks: frame f of plane p at plane[p] + f * ph[p] * stride[p].
+struct YuvIn {
+    const uint8_t *main[3] = {nullptr, nullptr, nullptr};
+    const uint8_t *ref[3] = {nullptr, nullptr, nullptr};
+    const uint8_t *halo[3] = {nullptr, nullptr, nullptr};
+    int stride[3] = {0, 0, 0}, ph[3] = {0, 0, 0}, pw[3] = {0, 0, 0};
+    vqa_fr_metrics *fr_out = nullptr;
+};
+
 int complexity_body(vqa_ctx *c, const uint8_t *bgr, int n, int h, int w, size_t frame_stride, const uint8_t *halo,
-                    int on_device, const vqa_cfg *cfg, vqa_frame_metrics *out, SideLoad *side);
+                    int on_device, const vqa_cfg *cfg, vqa_frame_metrics *out, SideLoad *side, const YuvIn *yuv);
+void fr_rows_from_sums(const unsigned long long *h_sse, const double *h_ssim, int n, const int32_t plane_w[3],
+                       const int32_t plane_h[3], vqa_fr_metrics *out);
 
 // An error can leave the chunk pipeline half enqueued (side stream forked and not joined, copies in
 // flight into the staging slots): drain all three streams before handing the context back, so the next
 // call starts from a quiescent state and the caller may free its buffers.
 int complexity_impl(vqa_ctx *c, const uint8_t *bgr, int n, int h, int w, size_t frame_stride, const uint8_t *halo,
-                    int on_device, const vqa_cfg *cfg, vqa_frame_metrics *out, SideLoad *side)
+                    int on_device, const vqa_cfg *cfg, vqa_frame_metrics *out, SideLoad *side, const YuvIn *yuv = nullptr)
 {
-    const int rc = complexity_body(c, bgr, n, h, w, frame_stride, halo, on_device, cfg, out, side);
+    const int rc = complexity_body(c, bgr, n, h, w, frame_stride, halo, on_device, cfg, out, side, yuv);
     if (rc != VQA_OK && c) {
         if (c->side_stream) cudaStreamSynchronize(c->side_stream);
         if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
@@ -328,18 +351,23 @@ int complexity_impl(vqa_ctx *c, const uint8_t *bgr, int n, int h, int w, size_t 
 }
 
 int complexity_body(vqa_ctx *c, const uint8_t *bgr, int n, int h, int w, size_t frame_stride, const uint8_t *halo,
-                    int on_device, const vqa_cfg *cfg, vqa_frame_metrics *out, SideLoad *side)
+                    int on_device, const vqa_cfg *cfg, vqa_frame_metrics *out, SideLoad *side, const YuvIn *yuv)
 {
     if (!c) return VQA_E_INVALID;
+#ifdef VQA_AB
     static const bool host_trace = getenv("VQA_HOST_TRACE") && atoi(getenv("VQA_HOST_TRACE"));
+#else
+    constexpr bool host_trace = false;
+#endif
     const auto t_host0 = std::chrono::steady_clock::now();
-    if (!bgr || !cfg || !out || n < 0 || h <= 0 || w <= 0)
+    if ((!bgr && !yuv) || !cfg || !out || n < 0 || h <= 0 || w <= 0)
         return set_err(c, VQA_E_INVALID, "vqa_complexity_frames: bad argument");
     if (n == 0) return VQA_OK;
     const int rw = cfg->resize_width, rh = cfg->resize_height;
     if (rw <= 0 || rh <= 0) return set_err(c, VQA_E_INVALID, "resize dimensions must be positive");
-    if (frame_stride < (size_t)h * w * 3) return set_err(c, VQA_E_INVALID, "frame_stride smaller than a frame");
+    if (!yuv && frame_stride < (size_t)h * w * 3) return set_err(c, VQA_E_INVALID, "frame_stride smaller than a frame");
     VQA_CUDA(c, cudaSetDevice(c->device));
+    const bool want_fr = yuv && yuv->ref[0];
     const unsigned mask = cfg->metrics_mask ? cfg->metrics_mask : VQA_M_ALL;
     const bool identity = (rw == w && rh == h);
     const size_t HW = (size_t)h * w, RR = (size_t)rw * rh, FB = HW * 3;
@@ -353,7 +381,7 @@ int complexity_body(vqa_ctx *c, const uint8_t *bgr, int n, int h, int w, size_t 
     const bool orb_general = want_orb && ow > 0 && !(ow == 64 && oh == 64);
     const bool orb_native = orb_general && ow == w && oh == h;
     const bool need_full_gray = want_motion || want_dct || (identity && (want_hist || want_edge)) || orb_native;
-    const int CH = std::min(n, pick_chunk(c, h, w, rw, rh, mask, cfg->orb_width, cfg->orb_height));
+    const int CH = std::min(n, pick_chunk(c, h, w, rw, rh, mask, cfg->orb_width, cfg->orb_height, yuv != nullptr));
 
     // per-clip result arrays on the device
     VQA_BUF(c, d_hent, float, "res.hent", n);
@@ -391,12 +419,39 @@ int complexity_body(vqa_ctx *c, const uint8_t *bgr, int n, int h, int w, size_t 
         VQA_BUF(c, in2, uint8_t, "in.bgr2", FB * CH);
         in[0] = in0; in[1] = in1; in[2] = in2;
     }
+    // yuv420p input: a staging slot holds the six plane stacks of a chunk (main Y,U,V | ref Y,U,V = 3 HW per
+    // frame, the size of a BGR frame); the BGR frames of the chunk are derived on the device into `conv`
+    uint8_t *conv = nullptr;
+    unsigned long long *d_sse = nullptr;
+    double *d_ssim = nullptr;
+    size_t ysz[3] = {0, 0, 0};                          // dense bytes per frame of each plane
+    if (yuv) {
+        for (int p = 0; p < 3; p++) ysz[p] = (size_t)yuv->ph[p] * yuv->pw[p];
+        if (ysz[0] + ysz[1] + ysz[2] > FB / 2) return set_err(c, VQA_E_INVALID, "yuv planes larger than a 4:2:0 frame");
+        VQA_BUF(c, cv_, uint8_t, "in.conv", FB * CH);
+        conv = cv_;
+        if (want_fr) {
+            VQA_BUF(c, se_, unsigned long long, "fr.sse", (size_t)3 * n);
+            VQA_BUF(c, ss_, double, "fr.ssim", (size_t)3 * n);
+            d_sse = se_; d_ssim = ss_;
+        }
+    }
+    // plane p (0..2 main, 3..5 ref) of the chunk staged in slot `sl` (capacity CH frames per stack)
+    auto slot_plane = [&](int sl, int p) -> uint8_t * {
+        size_t off = 0;
+        for (int q = 0; q < p; q++) off += ysz[q % 3] * CH;
+        return in[sl] + off;
+    };
     // Chunk schedule.  Device-resident input: equal chunks of CH frames.  Host input: the first chunk is
     // small and the sizes grow by ~1.3x up to CH, so the compute stream starts after the copy of 8 frames
     // instead of 48 (5 ms of a 95 ms clip) and every following copy still hides behind the previous chunk.
     std::vector<int> cstart;
     {
+#ifdef VQA_AB
         static const int ramp0 = getenv("VQA_RAMP0") ? atoi(getenv("VQA_RAMP0")) : 8;
+#else
+        constexpr int ramp0 = 8;
+#endif
         int pos = 0, sz = (!on_device && ramp0 > 0) ? std::min(CH, ramp0) : CH;
         while (pos < n) {
             cstart.push_back(pos);
@@ -406,10 +461,25 @@ int complexity_body(vqa_ctx *c, const uint8_t *bgr, int n, int h, int w, size_t 
         cstart.push_back(n);
     }
     const int nchunks = (int)cstart.size() - 1;
+#ifdef VQA_AB
     static const bool use_side = !(getenv("VQA_SIDE_STREAM") && atoi(getenv("VQA_SIDE_STREAM")) == 0);
+#else
+    constexpr bool use_side = true;
+#endif
     auto h2d_chunk = [&](int ci) -> int {
         const int s = cstart[ci], m = cstart[ci + 1] - s;
-        if (frame_stride == FB) {
+        if (yuv) {
+            for (int p = 0; p < (want_fr ? 6 : 3); p++) {
+                const int q = p % 3;
+                const uint8_t *sp = (p < 3 ? yuv->main[q] : yuv->ref[q]) + (size_t)s * yuv->ph[q] * yuv->stride[q];
+                if (yuv->stride[q] == yuv->pw[q]) {
+                    VQA_CUDA(c, cudaMemcpyAsync(slot_plane(ci % 3, p), sp, ysz[q] * m, cudaMemcpyHostToDevice, c->copy_stream));
+                } else {
+                    VQA_CUDA(c, cudaMemcpy2DAsync(slot_plane(ci % 3, p), yuv->pw[q], sp, yuv->stride[q], yuv->pw[q],
+                                                  (size_t)yuv->ph[q] * m, cudaMemcpyHostToDevice, c->copy_stream));
+                }
+            }
+        } else if (frame_stride == FB) {
             VQA_CUDA(c, cudaMemcpyAsync(in[ci % 3], bgr + (size_t)s * frame_stride, FB * m, cudaMemcpyHostToDevice, c->copy_stream));
         } else {
             VQA_CUDA(c, cudaMemcpy2DAsync(in[ci % 3], FB, bgr + (size_t)s * frame_stride, frame_stride, FB, m,
@@ -419,17 +489,35 @@ int complexity_body(vqa_ctx *c, const uint8_t *bgr, int n, int h, int w, size_t 
         return VQA_OK;
     };
     stage_begin(c, "all");
+    int rc;
     if (!on_device) {
         VQA_CUDA(c, cudaStreamSynchronize(c->stream));              // prior work may still read the staging slots
-        int rc = h2d_chunk(0);
-        if (rc) return rc;
+        if ((rc = h2d_chunk(0))) return rc;
     }
     bool has_prev = false;
-    int rc;
     // halo frame -> gray slot 0 (+ DCT coefficients slot 0)
-    if (halo && (want_motion || want_tdct)) {
+    const bool have_halo = halo || (yuv && yuv->halo[0]);
+    if (have_halo && (want_motion || want_tdct)) {
         const uint8_t *hsrc = halo;
-        if (!on_device) {
+        if (yuv) {                                     // halo planes -> (staged) -> BGR
+            VQA_BUF(c, hb, uint8_t, "in.halo", FB);
+            const uint8_t *hp[3] = {yuv->halo[0], yuv->halo[1], yuv->halo[2]};
+            int hst[3] = {yuv->stride[0], yuv->stride[1], yuv->stride[2]};
+            if (!on_device) {
+                VQA_BUF(c, hy, uint8_t, "in.halo_yuv", FB / 2 + 64);
+                size_t off = 0;
+                for (int p = 0; p < 3; p++) {
+                    VQA_CUDA(c, cudaMemcpy2DAsync(hy + off, yuv->pw[p], yuv->halo[p], yuv->stride[p], yuv->pw[p], yuv->ph[p],
+                                                  cudaMemcpyHostToDevice, c->stream));
+                    hp[p] = hy + off;
+                    hst[p] = yuv->pw[p];
+                    off += ysz[p];
+                }
+            }
+            const size_t hfs[3] = {0, 0, 0};
+            if ((rc = run_yuv420_to_bgr(c, hp, hst, hfs, 1, h, w, hb))) return rc;
+            hsrc = hb;
+        } else if (!on_device) {
             VQA_BUF(c, hb, uint8_t, "in.halo", FB);
             VQA_CUDA(c, cudaMemcpyAsync(hb, halo, FB, cudaMemcpyHostToDevice, c->stream));
             hsrc = hb;
@@ -449,9 +537,12 @@ int complexity_body(vqa_ctx *c, const uint8_t *bgr, int n, int h, int w, size_t 
         const int s = cstart[ci], m = cstart[ci + 1] - s;
         const uint8_t *src;
         size_t stride;
-        if (on_device) {
+        if (on_device && !yuv) {
             src = bgr + (size_t)s * frame_stride;
             stride = frame_stride;
+        } else if (on_device) {
+            src = conv;
+            stride = FB;
         } else {
             VQA_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copy[ci % 3], 0));
             if (ci + 1 < nchunks) {
@@ -460,8 +551,35 @@ int complexity_body(vqa_ctx *c, const uint8_t *bgr, int n, int h, int w, size_t 
             }
             if (side)                                     // a slice of the side load (proportional to the chunk) behind the next chunk's copy
                 if ((rc = side_issue(c, side, (size_t)((double)side->total * m / n) + 1))) return rc;
-            src = in[ci % 3];
+            src = yuv ? conv : in[ci % 3];
             stride = FB;
+        }
+        if (yuv) {
+            // planes of this chunk (staged or the caller's device stacks) -> BGR frames; PSNR/SSIM of the same planes
+            const uint8_t *mp[3], *rp[3];
+            int pst[3];
+            size_t pfs[3];
+            for (int p = 0; p < 3; p++) {
+                if (on_device) {
+                    pst[p] = yuv->stride[p];
+                    pfs[p] = (size_t)yuv->ph[p] * yuv->stride[p];
+                    mp[p] = yuv->main[p] + (size_t)s * pfs[p];
+                    rp[p] = want_fr ? yuv->ref[p] + (size_t)s * pfs[p] : nullptr;
+                } else {
+                    pst[p] = yuv->pw[p];
+                    pfs[p] = ysz[p];
+                    mp[p] = slot_plane(ci % 3, p);
+                    rp[p] = want_fr ? slot_plane(ci % 3, 3 + p) : nullptr;
+                }
+            }
+            stage_begin(c, "ingest");
+            if ((rc = run_yuv420_to_bgr(c, mp, pst, pfs, m, h, w, conv))) return rc;
+            stage_end(c, "ingest");
+            if (want_fr) {
+                stage_begin(c, "frscore");
+                if ((rc = run_psnr_ssim_planes(c, mp, rp, m, yuv->ph, yuv->pw, pst, pfs, d_sse + s, d_ssim + s, n))) return rc;
+                stage_end(c, "frscore");
+            }
         }
         uint8_t *Gc = G + HW;                       // slots 1..m
         // ---- ingest
@@ -549,9 +667,12 @@ int complexity_body(vqa_ctx *c, const uint8_t *bgr, int n, int h, int w, size_t 
         double *energy, *tdct, *mag;
         int *orb;
     } hr;
-    const size_t bytes = (size_t)n * (4 + 4 + 8 + 8 + 8 + 8 + 8 + 4) + 64;
-    uint8_t *hb = (uint8_t *)pinned_buf(c, "res.host", bytes);
+    const size_t bytes = (size_t)n * (4 + 4 + 8 + 8 + 8 + 8 + 8 + 4) + 64, fr_off = (bytes + 15) & ~(size_t)15;
+    const size_t fr_bytes = want_fr ? (size_t)n * 48 : 0;
+    uint8_t *hb = (uint8_t *)pinned_buf(c, "res.host", fr_off + fr_bytes);
     if (!hb) return VQA_E_NOMEM;
+    unsigned long long *h_sse = (unsigned long long *)(hb + fr_off);
+    double *h_ssim = (double *)(h_sse + 3 * (size_t)n);
     hr.edge = (unsigned long long *)hb;
     hr.sq = hr.edge + n;
     hr.energy = (double *)(hr.sq + n);
@@ -569,6 +690,10 @@ int complexity_body(vqa_ctx *c, const uint8_t *bgr, int n, int h, int w, size_t 
     if (want_motion) D2H(hr.mag, d_mag, double);
     if (want_orb) D2H(hr.orb, d_orb, int);
 #undef D2H
+    if (want_fr) {
+        VQA_CUDA(c, cudaMemcpyAsync(h_sse, d_sse, sizeof(unsigned long long) * 3 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+        VQA_CUDA(c, cudaMemcpyAsync(h_ssim, d_ssim, sizeof(double) * 3 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    }
     const auto t_host1 = std::chrono::steady_clock::now();
     VQA_CUDA(c, wait_stream(c));
     if (host_trace) {
@@ -580,7 +705,7 @@ int complexity_body(vqa_ctx *c, const uint8_t *bgr, int n, int h, int w, size_t 
     const float nanf_ = nanf("");
     for (int i = 0; i < n; i++) {
         vqa_frame_metrics &o = out[i];
-        const bool prev_ok = (i > 0) || (halo != nullptr);
+        const bool prev_ok = (i > 0) || have_halo;
         o.hist_entropy = (mask & VQA_M_HIST) ? hr.hent[i] : nanf_;
         o.color_entropy = (mask & VQA_M_COLOR) ? hr.cent[i] : nanf_;
         o.dct_energy = (mask & VQA_M_DCT) ? (float)hr.energy[i] : nanf_;
@@ -590,7 +715,31 @@ int complexity_body(vqa_ctx *c, const uint8_t *bgr, int n, int h, int w, size_t 
         o.edge_count = want_edge ? (int64_t)hr.edge[i] : -1;
         o.gray_sq_sum = want_dct ? hr.sq[i] : 0;
     }
+    if (want_fr) fr_rows_from_sums(h_sse, h_ssim, n, yuv->pw, yuv->ph, yuv->fr_out);
     return VQA_OK;
+}
+
+// per-plane sums -> the fields of FFmpeg's psnr / ssim stats lines (vf_psnr.c do_psnr, vf_ssim.c do_ssim)
+void fr_rows_from_sums(const unsigned long long *h_sse, const double *h_ssim, int n, const int32_t plane_w[3],
+                       const int32_t plane_h[3], vqa_fr_metrics *out)
+{
+    double area[3], tot = 0;
+    for (int p = 0; p < 3; p++) { area[p] = (double)plane_w[p] * plane_h[p]; tot += area[p]; }
+    for (int i = 0; i < n; i++) {
+        vqa_fr_metrics &o = out[i];
+        o.mse_avg = 0;
+        o.ssim_all = 0;
+        for (int p = 0; p < 3; p++) {
+            o.sse[p] = h_sse[(size_t)p * n + i];
+            o.mse[p] = (double)o.sse[p] / area[p];
+            o.psnr[p] = o.mse[p] == 0 ? INFINITY : 10.0 * log10(255.0 * 255.0 / o.mse[p]);
+            const int bw = plane_w[p] >> 2, bh = plane_h[p] >> 2;
+            o.ssim[p] = (bw > 1 && bh > 1) ? h_ssim[(size_t)p * n + i] / ((double)(bw - 1) * (bh - 1)) : 0.0;
+            o.mse_avg += o.mse[p] * (area[p] / tot);
+            o.ssim_all += o.ssim[p] * (area[p] / tot);
+        }
+        o.psnr_avg = o.mse_avg == 0 ? INFINITY : 10.0 * log10(255.0 * 255.0 / o.mse_avg);
+    }
 }
 
 }  // namespace
@@ -662,42 +811,45 @@ int vqa_psnr_ssim_planar(vqa_ctx *c, const uint8_t *const main_planes[3], const 
     VQA_BUF(c, d_sse, unsigned long long, "fr.sse", (size_t)3 * n);
     VQA_BUF(c, d_ssim, double, "fr.ssim", (size_t)3 * n);
     stage_begin(c, "frscore");
-    size_t up_bytes = 0;
-    for (int p = 0; p < 3; p++) up_bytes = std::max(up_bytes, (size_t)plane_h[p] * stride[p]);
-    const char *fr_env = getenv("VQA_FR_CHUNK");
-    const int CH = std::min(n, (fr_env && atoi(fr_env) > 0) ? atoi(fr_env) : 64);
-    uint8_t *buf[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
-    if (!on_device) {
-        VQA_BUF(c, a0, uint8_t, "fr.a0", up_bytes * CH);
-        VQA_BUF(c, b0, uint8_t, "fr.b0", up_bytes * CH);
-        VQA_BUF(c, a1, uint8_t, "fr.a1", up_bytes * CH);
-        VQA_BUF(c, b1, uint8_t, "fr.b1", up_bytes * CH);
-        buf[0][0] = a0; buf[0][1] = b0; buf[1][0] = a1; buf[1][1] = b1;
-    }
-    int rc, slot = 0;
-    if (!on_device) {
+    int rc;
+    if (on_device) {                                   // all frames, all three planes: one launch
+        size_t fs[3];
+        for (int p = 0; p < 3; p++) fs[p] = (size_t)plane_h[p] * stride[p];
+        if ((rc = run_psnr_ssim_planes(c, main_planes, ref_planes, n, plane_h, plane_w, stride, fs, d_sse, d_ssim, n))) return rc;
+    } else {
+        // host planes: chunks of <= 64 pairs through two staging slots (dense rows), copies on the copy stream
+        size_t psz[3], per = 0;
+        for (int p = 0; p < 3; p++) { psz[p] = ((size_t)plane_h[p] * plane_w[p] + 15) & ~(size_t)15; per += psz[p]; }
+        const int CH = std::min(n, 64);
+        VQA_BUF(c, s0, uint8_t, "fr.slot0", 2 * per * CH);
+        VQA_BUF(c, s1, uint8_t, "fr.slot1", 2 * per * CH);
+        uint8_t *slot[2] = {s0, s1};
         VQA_CUDA(c, cudaStreamSynchronize(c->stream));
         VQA_CUDA(c, cudaEventRecord(c->ev_done[0], c->stream));
         VQA_CUDA(c, cudaEventRecord(c->ev_done[1], c->stream));
-    }
-    for (int p = 0; p < 3; p++) {
-        const size_t pb = (size_t)plane_h[p] * stride[p];
-        for (int s = 0; s < n; s += CH, slot ^= 1) {
+        int sl = 0;
+        for (int s = 0; s < n; s += CH, sl ^= 1) {
             const int m = std::min(CH, n - s);
-            const uint8_t *a = main_planes[p] + (size_t)s * pb, *b = ref_planes[p] + (size_t)s * pb;
-            if (!on_device) {
-                // copy on the copy stream once the kernel that last used this slot is done
-                VQA_CUDA(c, cudaEventSynchronize(c->ev_done[slot]));     // never park a gated copy in the DMA queue
-                VQA_CUDA(c, cudaMemcpyAsync(buf[slot][0], a, pb * m, cudaMemcpyHostToDevice, c->copy_stream));
-                VQA_CUDA(c, cudaMemcpyAsync(buf[slot][1], b, pb * m, cudaMemcpyHostToDevice, c->copy_stream));
-                VQA_CUDA(c, cudaEventRecord(c->ev_copy[slot], c->copy_stream));
-                VQA_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copy[slot], 0));
-                a = buf[slot][0];
-                b = buf[slot][1];
-            }
-            if ((rc = run_psnr_ssim_plane(c, a, b, m, plane_h[p], plane_w[p], stride[p], d_sse + (size_t)p * n + s,
-                                          d_ssim + (size_t)p * n + s))) return rc;
-            if (!on_device) VQA_CUDA(c, cudaEventRecord(c->ev_done[slot], c->stream));
+            VQA_CUDA(c, cudaEventSynchronize(c->ev_done[sl]));     // never park a gated copy in the DMA queue
+            const uint8_t *ap[3], *bp[3];
+            int dst_stride[3];
+            size_t fs[3], off = 0;
+            for (int half = 0; half < 2; half++)
+                for (int p = 0; p < 3; p++) {
+                    const uint8_t *src = (half ? ref_planes[p] : main_planes[p]) + (size_t)s * plane_h[p] * stride[p];
+                    uint8_t *dst = slot[sl] + off;
+                    // frames are re-packed psz[p] bytes apart (16-byte aligned) with dense rows
+                    VQA_CUDA(c, cudaMemcpy2DAsync(dst, plane_w[p], src, stride[p], plane_w[p], (size_t)plane_h[p] * m,
+                                                  cudaMemcpyHostToDevice, c->copy_stream));
+                    (half ? bp : ap)[p] = dst;
+                    dst_stride[p] = plane_w[p];
+                    fs[p] = (size_t)plane_h[p] * plane_w[p];
+                    off += psz[p] * CH;
+                }
+            VQA_CUDA(c, cudaEventRecord(c->ev_copy[sl], c->copy_stream));
+            VQA_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copy[sl], 0));
+            if ((rc = run_psnr_ssim_planes(c, ap, bp, m, plane_h, plane_w, dst_stride, fs, d_sse + s, d_ssim + s, n))) return rc;
+            VQA_CUDA(c, cudaEventRecord(c->ev_done[sl], c->stream));
         }
     }
     stage_end(c, "frscore");
@@ -708,23 +860,56 @@ int vqa_psnr_ssim_planar(vqa_ctx *c, const uint8_t *const main_planes[3], const 
     VQA_CUDA(c, cudaMemcpyAsync(h_sse, d_sse, sizeof(unsigned long long) * 3 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
     VQA_CUDA(c, cudaMemcpyAsync(h_ssim, d_ssim, sizeof(double) * 3 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
     VQA_CUDA(c, wait_stream(c));
-    double area[3], tot = 0;
-    for (int p = 0; p < 3; p++) { area[p] = (double)plane_w[p] * plane_h[p]; tot += area[p]; }
-    for (int i = 0; i < n; i++) {
-        vqa_fr_metrics &o = out[i];
-        o.mse_avg = 0;
-        o.ssim_all = 0;
-        for (int p = 0; p < 3; p++) {
-            o.sse[p] = h_sse[(size_t)p * n + i];
-            o.mse[p] = (double)o.sse[p] / area[p];
-            o.psnr[p] = o.mse[p] == 0 ? INFINITY : 10.0 * log10(255.0 * 255.0 / o.mse[p]);
-            const int bw = plane_w[p] >> 2, bh = plane_h[p] >> 2;
-            o.ssim[p] = (bw > 1 && bh > 1) ? h_ssim[(size_t)p * n + i] / ((double)(bw - 1) * (bh - 1)) : 0.0;
-            o.mse_avg += o.mse[p] * (area[p] / tot);
-            o.ssim_all += o.ssim[p] * (area[p] / tot);
-        }
-        o.psnr_avg = o.mse_avg == 0 ? INFINITY : 10.0 * log10(255.0 * 255.0 / o.mse_avg);
+    fr_rows_from_sums(h_sse, h_ssim, n, plane_w, plane_h, out);
+    return VQA_OK;
+}
+
+// Both halves of one clip from ONE upload of yuv420p planes.  The reference compares the
+// source with its encode (run_ffmpeg_metrics(input, encoded), video_processing.py:216) and then analyses the
+// ENCODED file (calculate_average_scene_complexity(encoded), :242) -- the BGR frames cv2.VideoCapture hands it
+// are libswscale's conversion of the encode's yuv420p planes, reproduced bit-exactly on the device (yuv.cu).
+int vqa_analyze_clip_yuv420(vqa_ctx *c, const uint8_t *const main_planes[3], const uint8_t *const ref_planes[3],
+                            const int32_t stride[3], int n, int h, int w, const uint8_t *const halo_planes[3],
+                            int on_device, const vqa_cfg *cfg, vqa_frame_metrics *rows_out, vqa_fr_metrics *fr_out)
+{
+    if (!c) return VQA_E_INVALID;
+    if (!main_planes || !stride || !cfg || !rows_out || n < 0 || h <= 0 || w <= 0)
+        return set_err(c, VQA_E_INVALID, "vqa_analyze_clip_yuv420: bad argument");
+    if ((h | w) & 1) return set_err(c, VQA_E_UNSUPPORTED, "vqa_analyze_clip_yuv420: yuv420p frames must have even sizes (got %dx%d)", w, h);
+    if (ref_planes && !fr_out) return set_err(c, VQA_E_INVALID, "vqa_analyze_clip_yuv420: ref planes without fr_out");
+    if (n == 0) return VQA_OK;
+    YuvIn y;
+    for (int p = 0; p < 3; p++) {
+        y.pw[p] = p ? w / 2 : w;
+        y.ph[p] = p ? h / 2 : h;
+        y.stride[p] = stride[p];
+        if (!main_planes[p] || stride[p] < y.pw[p] || (ref_planes && !ref_planes[p]) || (halo_planes && !halo_planes[p]))
+            return set_err(c, VQA_E_INVALID, "vqa_analyze_clip_yuv420: bad plane %d", p);
+        y.main[p] = main_planes[p];
+        y.ref[p] = ref_planes ? ref_planes[p] : nullptr;
+        y.halo[p] = halo_planes ? halo_planes[p] : nullptr;
     }
+    y.fr_out = fr_out;
+    return complexity_impl(c, nullptr, n, h, w, 0, nullptr, on_device, cfg, rows_out, nullptr, &y);
+}
+
+int vqa_debug_yuv2bgr(vqa_ctx *c, const uint8_t *y, const uint8_t *u, const uint8_t *v, int h, int w, uint8_t *bgr_out)
+{
+    if (!c || !y || !u || !v || !bgr_out || h <= 0 || w <= 0) return VQA_E_INVALID;
+    VQA_CUDA(c, cudaSetDevice(c->device));
+    const size_t HW = (size_t)h * w, CW = (size_t)(h / 2) * (w / 2);
+    VQA_BUF(c, d_in, uint8_t, "dbg.in", HW + 2 * CW + 64);
+    VQA_BUF(c, d_out, uint8_t, "dbg.out", HW * 4);
+    VQA_CUDA(c, cudaMemcpyAsync(d_in, y, HW, cudaMemcpyHostToDevice, c->stream));
+    VQA_CUDA(c, cudaMemcpyAsync(d_in + HW, u, CW, cudaMemcpyHostToDevice, c->stream));
+    VQA_CUDA(c, cudaMemcpyAsync(d_in + HW + CW, v, CW, cudaMemcpyHostToDevice, c->stream));
+    const uint8_t *pl[3] = {d_in, d_in + HW, d_in + HW + CW};
+    const int st[3] = {w, w / 2, w / 2};
+    const size_t fs[3] = {0, 0, 0};
+    int rc = run_yuv420_to_bgr(c, pl, st, fs, 1, h, w, d_out);
+    if (rc) return rc;
+    VQA_CUDA(c, cudaMemcpyAsync(bgr_out, d_out, HW * 3, cudaMemcpyDeviceToHost, c->stream));
+    VQA_CUDA(c, cudaStreamSynchronize(c->stream));
     return VQA_OK;
 }
 

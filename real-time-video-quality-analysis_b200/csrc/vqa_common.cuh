@@ -60,6 +60,8 @@ struct vqa_ctx {
     size_t free_cached = 0;
     void *umma = nullptr;                         // tensor-map cache of the tcgen05 DCT (dct_umma.cu)
     void *orb = nullptr;                          // pyramid geometry cache of the general-size ORB (orb.cu)
+    void *comm = nullptr;                         // ncclComm_t owned by the context (vqa_comm_init, comm.cu)
+    int comm_rank = 0, comm_world = 0;
 };
 
 namespace vqa {
@@ -208,8 +210,16 @@ void dct_umma_release(vqa_ctx *c);
 int run_farneback(vqa_ctx *c, const uint8_t *gray /* [n+1][h][w] */, int npairs, int h, int w,
                   double *mag_sum /* [npairs] dev: sum |flow| */, float *flow_out /* optional, level-0 flow of pair 0.. */);
 // psnr_ssim.cu
-int run_psnr_ssim_plane(vqa_ctx *c, const uint8_t *a, const uint8_t *b, int n, int h, int w, int stride,
+int run_psnr_ssim_plane(vqa_ctx *c, const uint8_t *a, const uint8_t *b, int n, int h, int w, int stride, size_t frame_stride,
                         unsigned long long *sse /* [n] */, double *ssim_sum /* [n] */);
+int run_psnr_ssim_planes(vqa_ctx *c, const uint8_t *const a[3], const uint8_t *const b[3], int n, const int plane_h[3],
+                         const int plane_w[3], const int stride[3], const size_t frame_stride[3],
+                         unsigned long long *sse /* [3][out_pitch] */, double *ssim_sum /* [3][out_pitch] */, int out_pitch);
+// yuv.cu
+int run_yuv420_to_bgr(vqa_ctx *c, const uint8_t *const planes[3], const int stride[3], const size_t frame_stride[3],
+                      int n, int h, int w, uint8_t *bgr /* [n][h][w][3] dense */);
+// comm.cu
+void comm_release(vqa_ctx *c);
 // stats.cu
 int run_framerate(vqa_ctx *c, const double *ts_dev, int n, double *fps_dev);
 int run_ewm_partial(vqa_ctx *c, const double *x_dev, int n_local, long long offset, long long total, double alpha,

@@ -62,19 +62,41 @@ def local_partials(rows, a: int, k_frames: int, alpha: float, partial_fn):
     return out
 
 
-def reduce_partials(partials: np.ndarray, int_totals: np.ndarray, group=None, device=None):
-    """Sum the per-rank partial sums (float64) and integer side totals (int64) over the process
-    group; returns numpy arrays.  One collective each, payload < 100 bytes."""
+def init_context_comm(ctx, group=None):
+    """Give ``ctx`` its own NCCL communicator over the ranks of the torch process group (vqa_comm_init):
+    rank 0 creates the unique id inside the library and the group broadcasts its 128 bytes.  After this,
+    ``reduce_partials(..., ctx=ctx)`` runs as ONE ncclAllReduce inside libvqa_b200.so (vqa_clip_reduce) --
+    the call a host without any NCCL binding of its own would make."""
+    import torch.distributed as dist
+    from . import _native as N
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    box = [N.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    ctx.comm_init(rank, world, box[0])
+    return ctx
+
+
+def reduce_partials(partials: np.ndarray, int_totals: np.ndarray, group=None, device=None, ctx=None):
+    """Sum the per-rank partial sums (float64) and integer side totals (int64) over all ranks; returns
+    numpy arrays.  With a context that owns a communicator (``init_context_comm``) this is vqa_clip_reduce:
+    one fused buffer, one ncclAllReduce on the context's stream.  Otherwise (the gloo CPU tests of the
+    host logic, or a caller that brought only a torch group) one torch all-reduce of the same fused
+    float64 buffer -- integers ride as doubles, exact below 2^53 (checked)."""
+    if ctx is not None and getattr(ctx, "comm_world", 0) > 1:
+        return ctx.clip_reduce(partials, int_totals)
     import torch
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return partials, int_totals
     dev = device if device is not None else ("cuda" if dist.get_backend(group) == "nccl" else "cpu")
-    f = torch.as_tensor(partials, dtype=torch.float64, device=dev)
-    i = torch.as_tensor(int_totals, dtype=torch.int64, device=dev)
-    dist.all_reduce(f, op=dist.ReduceOp.SUM, group=group)
-    dist.all_reduce(i, op=dist.ReduceOp.SUM, group=group)
-    return f.cpu().numpy(), i.cpu().numpy()
+    p = np.asarray(partials, dtype=np.float64)
+    i = np.asarray(int_totals, dtype=np.int64)
+    if i.size and np.abs(i).max() >= 2 ** 53 // dist.get_world_size(group):
+        raise OverflowError("integer total too large for an exact reduce")
+    buf = torch.as_tensor(np.concatenate([p.ravel(), i.ravel().astype(np.float64)]), dtype=torch.float64, device=dev)
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    out = buf.cpu().numpy()
+    return out[:p.size].reshape(p.shape), np.rint(out[p.size:]).astype(np.int64).reshape(i.shape)
 
 
 def gather_rows(rows, group=None, device=None):
@@ -136,7 +158,7 @@ def sharded_average_scene_complexity(local_frames, a: int, k_frames: int, resize
     partials = local_partials(rows, a, k_frames, alpha, ctx.ewm_partial)
     ints = np.array([int(rows["edge_count"][max(1 - a, 0):].sum()), int(rows["orb_count"][max(1 - a, 0):].sum()),
                      len(rows)], dtype=np.int64)
-    partials, ints = reduce_partials(partials, ints, group)
+    partials, ints = reduce_partials(partials, ints, group, ctx=ctx)
     fps = ctx.framerate_series(timestamps_ms) if len(timestamps_ms) > 1 else np.zeros(0)
     fr = ctx.ewm_partial(fps, 0, len(fps), alpha) if len(fps) else float("nan")
     return finalize(partials, k_frames, fr), ints
@@ -199,22 +221,36 @@ def multi_clip_partials(plan_for_rank, rows_of, clip_frames, alpha: float, parti
 
 
 def sharded_multi_clip_scene_complexity(clips, resize_width: int, resize_height: int, timestamps_ms, rank: int, world: int,
-                                        alpha: float = 0.8, group=None, ctx=None):
+                                        alpha: float = 0.8, group=None, ctx=None, clip_frames=None):
     """All clips of a batch over all ranks: ONE all-reduce of [n_clips x 7] doubles (+ [n_clips x 3]
     integers) closes every clip.  ``clips[c]`` is the (K_c,h,w,3) uint8 array (host or CUDA tensor) of
     sampled frames -- only the shards of ``plan_clip_shards(...)[rank]`` are touched, so a rank may
-    pass ``None`` for clips it does not own.  Returns a list of 8-tuples in the reference's order."""
+    pass ``None`` for clips it does not own.  ``clip_frames[c]`` = K_c, the number of SAMPLED FRAMES of clip c
+    (floor(N/I), App. B) -- required whenever a rank holds ``None`` for a clip, and NOT the same as
+    ``len(timestamps_ms[c])`` (ceil(N/I) entries: one more than frames when N % I != 0).  Returns a list of
+    8-tuples in the reference's order."""
     from . import _native as N
     ctx = ctx or N.get_context()
-    clip_frames = [len(t) for t in timestamps_ms]
+    if clip_frames is None:
+        if any(c is None for c in clips):
+            raise ValueError("clip_frames is required when some clips are not held by this rank")
+        clip_frames = [len(c) for c in clips]
+    clip_frames = [int(k) for k in clip_frames]
+    if len(clip_frames) != len(clips) or len(timestamps_ms) != len(clips):
+        raise ValueError("clips, clip_frames and timestamps_ms must have one entry per clip")
+    for c, fr in enumerate(clips):
+        if fr is not None and len(fr) != clip_frames[c]:
+            raise ValueError(f"clip {c}: {len(fr)} frames held but clip_frames says {clip_frames[c]}")
     plan = plan_clip_shards(clip_frames, world)[rank]
 
     def rows_of(clip, a, b):
         fr = clips[clip]
+        if fr is None:
+            raise ValueError(f"rank {rank} owns frames [{a},{b}) of clip {clip} but was not given the clip")
         return ctx.complexity_frames(fr[a:b], resize_width, resize_height, N.M_ALL, halo=fr[a - 1] if a > 0 else None)
 
     partials, ints = multi_clip_partials(plan, rows_of, clip_frames, alpha, ctx.ewm_partial)
-    partials, ints = reduce_partials(partials, ints, group)
+    partials, ints = reduce_partials(partials, ints, group, ctx=ctx)
     out = []
     for c, ts in enumerate(timestamps_ms):
         fps = ctx.framerate_series(ts) if len(ts) > 1 else np.zeros(0)

@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol(vqa):
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in vqa_b200.h but not exported"
     assert sorted(set(declared)) == sorted(set(N.EXPORTS)), "binding and header disagree on the entry points"
-    assert lib.vqa_abi_version() == N.ABI_VERSION == 2
+    assert lib.vqa_abi_version() == N.ABI_VERSION == 3
 
 
 def test_struct_layouts_match_header(vqa, tmp_path):

@@ -207,3 +207,54 @@ def test_two_rank_gloo_multi_clip_reduce(vqa, small_clip, tmp_path, cuts):
         res = SH.finalize(partials[c], len(clip), want[7])
         np.testing.assert_allclose(res, want, rtol=1e-6)
         assert ints[c, 0] == sum(RP.o_edge(f, 64, 64) for f in clip[1:]) and ints[c, 2] == len(clip)
+
+
+def test_multi_clip_needs_frame_counts_not_timestamp_counts(vqa):
+    """App. B: a clip of N source frames sampled every I has floor(N/I) sampled frames but ceil(N/I) timestamps, so
+    with N % I != 0 there is one more timestamp than frames.  The clip plan must be built from the FRAME count
+    (ADVICE r1): `clip_frames` is explicit, inconsistent inputs are refused before any device work."""
+    from rtvqa_b200 import sharding as SH
+    frames = np.zeros((3, 8, 8, 3), np.uint8)                 # N = 35, I = 10 -> 3 sampled frames, 4 timestamps
+    ts = [0.0, 333.3, 666.7, 1000.0]
+    with pytest.raises(ValueError, match="clip_frames is required"):
+        SH.sharded_multi_clip_scene_complexity([None], 64, 64, [ts], rank=0, world=1, ctx=object())
+    with pytest.raises(ValueError, match="frames held but clip_frames says"):
+        SH.sharded_multi_clip_scene_complexity([frames], 64, 64, [ts], rank=0, world=1, ctx=object(), clip_frames=[len(ts)])
+    with pytest.raises(ValueError, match="one entry per clip"):
+        SH.sharded_multi_clip_scene_complexity([frames], 64, 64, [ts, ts], rank=0, world=1, ctx=object(), clip_frames=[3])
+    # the plan follows the frame count: 3 frames over 4 ranks leave the last rank empty, never a phantom 4th frame
+    plan = SH.plan_clip_shards([3], 4)
+    assert [p for p in plan if p] == [[(0, 0, 1)], [(0, 1, 2)], [(0, 2, 3)]]
+
+
+def _fused_worker(rank, world, port, out_path):
+    import torch.distributed as dist
+    import rtvqa_b200  # noqa: F401
+    from rtvqa_b200 import sharding as SH
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    p = np.arange(14, dtype=np.float64).reshape(2, 7) * (rank + 1) + 0.125
+    i = np.array([[2 ** 40 + rank, 7, 3], [5, rank, 1]], dtype=np.int64)
+    gp, gi = SH.reduce_partials(p, i)
+    try:
+        SH.reduce_partials(p, np.array([2 ** 53], dtype=np.int64))
+        overflow = False
+    except OverflowError:
+        overflow = True
+    if rank == 0:
+        np.savez(out_path, p=gp, i=gi, overflow=overflow)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_fused_reduce_keeps_shapes_and_exact_integers(vqa, tmp_path):
+    """reduce_partials moves ONE fused float64 buffer (doubles + integers as doubles): shapes survive, integers
+    stay exact, and an integer that could round is refused instead of rounded."""
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "fused.npz")
+    mp.spawn(_fused_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    z = np.load(out)
+    assert z["p"].shape == (2, 7) and z["i"].shape == (2, 3) and z["i"].dtype == np.int64
+    np.testing.assert_array_equal(z["p"], np.arange(14, dtype=np.float64).reshape(2, 7) * 3 + 0.25)
+    assert z["i"].tolist() == [[2 ** 41 + 1, 14, 6], [10, 1, 2]] and bool(z["overflow"])
