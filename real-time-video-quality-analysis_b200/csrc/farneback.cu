@@ -258,8 +258,8 @@ constexpr int PE_P = 76;                         // tile pitch (64 + 2*5 = 74, p
 
 // FarnebackPolyExp.  Register-blocked: every work item produces 4 adjacent columns from 128-bit
 // shared-memory reads (vertical pass: 11 LDS.128 per 4 outputs, horizontal pass: 12 LDS.128 per 4
-// outputs).  The vertical pass is float like OpenCV's; the horizontal accumulators are double like
-// OpenCV's (ACC = double) or float (ACC = float, selectable for A/B: VQA_PE_F32=1).
+// outputs).  Both passes accumulate in float (OpenCV's horizontal accumulators are double; against the
+// unmodified reference the clip mean moves by < 1e-7 rel, profiles/r01_notes.md).
 // A block walks PE_STRIP vertically adjacent tiles; the pixel tile is double-buffered and filled with
 // 4-byte cp.async (any alignment, border clamp in the address), so the loads of tile k+1 fly while
 // tile k is computed (the synchronous version sat 63 % of its stall samples on the tile load).
@@ -277,7 +277,6 @@ __device__ __forceinline__ void pe_load_tile(float (*tile)[PE_P], const float *_
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
-template <typename ACC>
 __global__ void __launch_bounds__(256)
 k_fb_polyexp(const float *__restrict__ I, int h, int w, PolyConst pc, float *__restrict__ R)
 {
@@ -343,24 +342,24 @@ k_fb_polyexp(const float *__restrict__ I, int h, int w, PolyConst pc, float *__r
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     const int c = j + PE_R;
-                    const ACC g0 = pc.g[PE_R];
-                    ACC b1 = a0[c] * g0, b2 = 0, b3 = a1[c] * g0, b4 = 0, b5 = a2[c] * g0, b6 = 0;
+                    const float g0 = pc.g[PE_R];
+                    float b1 = a0[c] * g0, b2 = 0, b3 = a1[c] * g0, b4 = 0, b5 = a2[c] * g0, b6 = 0;
 #pragma unroll
                     for (int k = 1; k <= PE_R; k++) {
-                        const ACC gk = pc.g[PE_R + k], xgk = pc.xg[PE_R + k], xxgk = pc.xxg[PE_R + k];
-                        const ACC tg = (ACC)(a0[c + k] + a0[c - k]);
+                        const float gk = pc.g[PE_R + k], xgk = pc.xg[PE_R + k], xxgk = pc.xxg[PE_R + k];
+                        const float tg = (a0[c + k] + a0[c - k]);
                         b1 += tg * gk;
                         b4 += tg * xxgk;
-                        b2 += (ACC)(a0[c + k] - a0[c - k]) * xgk;
-                        b3 += (ACC)(a1[c + k] + a1[c - k]) * gk;
-                        b6 += (ACC)(a1[c + k] - a1[c - k]) * xgk;
-                        b5 += (ACC)(a2[c + k] + a2[c - k]) * gk;
+                        b2 += (a0[c + k] - a0[c - k]) * xgk;
+                        b3 += (a1[c + k] + a1[c - k]) * gk;
+                        b6 += (a1[c + k] - a1[c - k]) * xgk;
+                        b5 += (a2[c + k] + a2[c - k]) * gk;
                     }
-                    o[0][j] = (float)(b3 * (ACC)pc.ig11);
-                    o[1][j] = (float)(b2 * (ACC)pc.ig11);
-                    o[2][j] = (float)(b1 * (ACC)pc.ig03 + b5 * (ACC)pc.ig33);
-                    o[3][j] = (float)(b1 * (ACC)pc.ig03 + b4 * (ACC)pc.ig33);
-                    o[4][j] = (float)(b6 * (ACC)pc.ig55);
+                    o[0][j] = (float)(b3 * (float)pc.ig11);
+                    o[1][j] = (float)(b2 * (float)pc.ig11);
+                    o[2][j] = (float)(b1 * (float)pc.ig03 + b5 * (float)pc.ig33);
+                    o[3][j] = (float)(b1 * (float)pc.ig03 + b4 * (float)pc.ig33);
+                    o[4][j] = (float)(b6 * (float)pc.ig55);
                 }
                 float *dst = R + (size_t)frame * 5 * plane + (size_t)gy * w + gx0;
                 const bool vec = (w & 3) == 0 && gx0 + 4 <= w;          // planes are 256-byte aligned, w % 4 == 0 keeps rows aligned
@@ -513,62 +512,19 @@ k_fb_matrices(const float *__restrict__ R, const float2 *__restrict__ flow, int 
     for (int c = 0; c < 5; c++) dst[c * FB_MS] = m[c];
 }
 
-// UpdateMatrices with the flow read from memory, 4 adjacent pixels per thread: R0, flow and M move
-// as 128-bit accesses (wider DRAM bursts per plane, 4x fewer requests); the R1 gathers stay scalar.
-// Requires w % 4 == 0 (planes are 256-byte aligned).
-template <int INIT>
-__global__ void __launch_bounds__(256)
-k_fb_matrices_v4(const float *__restrict__ R, const float2 *__restrict__ flow, int h, int w, float *__restrict__ M,
-                 const float2 *__restrict__ prev, int ph, int pw)
-{
-    const int pair = blockIdx.z;
-    const int x = (blockIdx.x * 32 + (threadIdx.x & 31)) * 4, y = blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (x >= w || y >= h) return;
-    const size_t plane = (size_t)h * w, o = (size_t)y * w + x;
-    const float *R0 = R + (size_t)pair * 5 * plane, *R1 = R0 + 5 * plane;
-    float4 q[5];
-#pragma unroll
-    for (int c = 0; c < 5; c++) q[c] = __ldg(reinterpret_cast<const float4 *>(R0 + c * plane + o));
-    float2 f[4];
-    if (INIT == 0) {
-        const float4 f01 = __ldg(reinterpret_cast<const float4 *>(flow + (size_t)pair * plane + o));
-        const float4 f23 = __ldg(reinterpret_cast<const float4 *>(flow + (size_t)pair * plane + o + 2));
-        f[0] = make_float2(f01.x, f01.y); f[1] = make_float2(f01.z, f01.w);
-        f[2] = make_float2(f23.x, f23.y); f[3] = make_float2(f23.z, f23.w);
-    } else if (INIT == 1) {
-#pragma unroll
-        for (int j = 0; j < 4; j++) f[j] = fb_upsampled_flow(prev + (size_t)pair * ph * pw, ph, pw, x + j, y, h, w);
-    } else {
-#pragma unroll
-        for (int j = 0; j < 4; j++) f[j] = make_float2(0.f, 0.f);
-    }
-    float m[4][5];
-#define QJ(c, j) (j == 0 ? q[c].x : j == 1 ? q[c].y : j == 2 ? q[c].z : q[c].w)
-#pragma unroll
-    for (int j = 0; j < 4; j++)
-        fb_matrix_core(QJ(0, j), QJ(1, j), QJ(2, j), QJ(3, j), QJ(4, j), R1, plane, x + j, y, h, w, f[j], m[j]);
-#undef QJ
-    float *dst = M + (size_t)pair * fb_m_pair_floats(h, w) + fb_m_index((unsigned)(y * w + x));
-#pragma unroll
-    for (int c = 0; c < 5; c++)
-        *reinterpret_cast<float4 *>(dst + c * FB_MS) = make_float4(m[0][c], m[1][c], m[2][c], m[3][c]);
-}
-
-// UpdateMatrices, "transposed gather" variant of k_fb_matrices_v4<0>.  ncu on v4: the 20 scalar R1
-// gathers per pixel are issued with the lanes of a warp 16 bytes apart (each lane owns 4 adjacent pixels),
-// so every gather instruction touches 16-20 sectors of which 4 bytes each are used -- 637 M sectors per
-// level-0 launch against 237 M for the one-pixel-per-lane kernel, L1 data pipe 88 % busy.  Here R0, flow
-// and M still move as 128-bit accesses (4 pixels per lane), but the per-pixel work runs with the lanes of
+// UpdateMatrices with the flow read from memory, "transposed gather".  A plain 4-pixels-per-lane kernel
+// (round 1's k_fb_matrices_v4, removed) issues the 20 scalar R1 gathers per pixel with the lanes of a warp
+// 16 bytes apart, so every gather instruction touches 16-20 sectors of which 4 bytes each are used -- 637 M
+// sectors per level-0 launch against 237 M for the one-pixel-per-lane kernel, L1 data pipe 88 % busy.  Here
+// R0, flow and M move as 128-bit accesses (4 pixels per lane), but the per-pixel work runs with the lanes of
 // a warp on 32 ADJACENT pixels (4 rounds per 128-pixel row segment): the operands are transposed through
 // a per-warp shared-memory tile (conflict-free both ways), the gathers of a warp then fall into 1-2
 // cache lines, and the results go back through the same tile.  Arithmetic per pixel is fb_matrix_core,
-// unchanged, so M is bit-identical to v4's.  Requires w % 4 == 0.
-// INIT 0: flow read from memory; INIT 1: flow up-sampled on the fly from the coarser level (first
-// UpdateMatrices of a level), one pixel per lane like the gathers.
-template <int INIT>
+// unchanged, so M is bit-identical to k_fb_matrices<0>'s.  Requires w % 4 == 0.  Flow read from memory (the first
+// UpdateMatrices of a level up-samples the coarser flow in k_fb_matrices<1>: a transposed variant of that
+// measured 25 % slower at 63 registers).
 __global__ void __launch_bounds__(256)
-k_fb_matrices_t4(const float *__restrict__ R, const float2 *__restrict__ flow, int h, int w, float *__restrict__ M,
-                 const float2 *__restrict__ prev, int ph, int pw)
+k_fb_matrices_t4(const float *__restrict__ R, const float2 *__restrict__ flow, int h, int w, float *__restrict__ M)
 {
     __shared__ __align__(16) float tile[8][7 * 128];               // per warp: 5 planes of R0 | interleaved flow (256)
     const int pair = blockIdx.z, lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
@@ -582,10 +538,8 @@ k_fb_matrices_t4(const float *__restrict__ R, const float2 *__restrict__ flow, i
 #pragma unroll
         for (int c = 0; c < 5; c++)
             *reinterpret_cast<float4 *>(t + c * 128 + lane * 4) = __ldg(reinterpret_cast<const float4 *>(R0 + c * plane + o));
-        if (INIT == 0) {
-            *reinterpret_cast<float4 *>(t + 640 + lane * 8) = __ldg(reinterpret_cast<const float4 *>(flow + (size_t)pair * plane + o));
-            *reinterpret_cast<float4 *>(t + 640 + lane * 8 + 4) = __ldg(reinterpret_cast<const float4 *>(flow + (size_t)pair * plane + o + 2));
-        }
+        *reinterpret_cast<float4 *>(t + 640 + lane * 8) = __ldg(reinterpret_cast<const float4 *>(flow + (size_t)pair * plane + o));
+        *reinterpret_cast<float4 *>(t + 640 + lane * 8 + 4) = __ldg(reinterpret_cast<const float4 *>(flow + (size_t)pair * plane + o + 2));
     }
     __syncwarp();
     float m[4][5];
@@ -593,8 +547,7 @@ k_fb_matrices_t4(const float *__restrict__ R, const float2 *__restrict__ flow, i
     for (int j = 0; j < 4; j++) {
         const int g = 32 * j + lane;                                 // pixel of this lane in round j
         if (xw + g < w) {
-            const float2 f = INIT == 0 ? *reinterpret_cast<const float2 *>(t + 640 + 2 * g)
-                                       : fb_upsampled_flow(prev + (size_t)pair * ph * pw, ph, pw, xw + g, y, h, w);
+            const float2 f = *reinterpret_cast<const float2 *>(t + 640 + 2 * g);
             fb_matrix_core(t[g], t[128 + g], t[256 + g], t[384 + g], t[512 + g], R1, plane, xw + g, y, h, w, f, m[j]);
         } else {
 #pragma unroll
@@ -634,17 +587,6 @@ constexpr int MS_W = 128, MS_OUT = 112, MS_R = 7, MS_H = 96, MS_SEG = 8;
 __device__ __forceinline__ int ms_sw(int i) { return i + ((i >> 5) << 2); }
 constexpr int MS_VP = 144;
 
-// running sum kept as an unevaluated float pair (hi + lo): Knuth's TwoSum adds x exactly into hi and
-// the rounding error into lo, ~48 significant bits with FP32 adds only
-__device__ __forceinline__ void ff_add(float &hi, float &lo, float x)
-{
-    const float s = __fadd_rn(hi, x);
-    const float bb = __fsub_rn(s, hi);
-    const float e = __fadd_rn(__fsub_rn(hi, __fsub_rn(s, bb)), __fsub_rn(x, bb));
-    hi = s;
-    lo = __fadd_rn(lo, e);
-}
-
 // FarnebackUpdateFlow_Blur, column-marching (see above).  On B200 this kernel is bound by warp
 // instruction ISSUE (ncu: issue slots 78 % busy, 3 eligible warps per cycle; DRAM 46 %, L1 70 %), so
 // the design minimises instructions per output, in this order of discovery (profiles/r01_notes.md):
@@ -653,21 +595,14 @@ __device__ __forceinline__ void ff_add(float &hi, float &lo, float x)
 //     no error persists) with a dependent chain of 8;
 //   * the 2x2 solve runs in float with FMA-recovered product errors (no conversions);
 //   * M in a layout whose plane offsets are compile-time constants (ten loads from two pointers);
-//   * VACC 1 (default): the vertical 15-row running sums are DOUBLE registers: 10 DADD + 15
-//     conversions per row.  A plain float running sum would keep eps*|edge value| of error in flat
-//     areas below strong edges (OpenCV uses double here too).  VACC 0 keeps them as float-float
-//     pairs updated with TwoSum on the FMA pipe: no XU/FP64 work but 75 FADD per row, 8 % slower
-//     now that the solve no longer loads the XU pipe (it was the faster variant before that).
-//
-// EPI 0: the new flow is stored (last iteration of a level; on level 0 the caller may ask for
-//        sum |flow| instead).  EPI 1 (VQA_FB_EPI=1, off by default: 7 % slower, the gather latency of the
-//        epilogue is exposed once per row): the flow never leaves the registers -- the UpdateMatrices of
-//        the NEXT iteration is pointwise in the pixel, so it is evaluated right here from R0/R1 and the
-//        fresh flow and written to the other M buffer (saves the flow round trip and one launch).
-template <int EPI, int VACC>
+//   * the vertical 15-row running sums are DOUBLE registers: 10 DADD + 15 conversions per row.  A plain
+//     float running sum would keep eps*|edge value| of error in flat areas below strong edges (OpenCV
+//     uses double here too); float-float pairs updated with TwoSum measured 8 % slower, evaluating the
+//     next UpdateMatrices in the epilogue 7 % slower (profiles/r01_notes.md; both variants removed).
+// The new flow is stored; on the last iteration of level 0 the caller may ask for sum |flow| instead.
 __global__ void __launch_bounds__(MS_W)
 k_fb_blur_solve(const float *__restrict__ M, int h, int w, float2 *__restrict__ flow, int rows_per_block,
-                double *__restrict__ mag_sum, int write_flow, const float *__restrict__ R, float *__restrict__ Mnext)
+                double *__restrict__ mag_sum, int write_flow)
 {
     __shared__ __align__(16) float row[5][MS_VP];
     __shared__ __align__(16) float hs[5][MS_VP];
@@ -677,17 +612,14 @@ k_fb_blur_solve(const float *__restrict__ M, int h, int w, float2 *__restrict__ 
     const int sx0 = blockIdx.x * MS_OUT, y0 = blockIdx.y * rows_per_block;
     const int gx = clampi(sx0 - 8 + t, 0, w - 1);
     const int y_end = min(y0 + rows_per_block, h);
-    float vh[5], vl[5];
     double vd[5];
 #pragma unroll
-    for (int c = 0; c < 5; c++) { vh[c] = vl[c] = 0.f; vd[c] = 0.0; }
+    for (int c = 0; c < 5; c++) vd[c] = 0.0;
     for (int k = -MS_R; k <= MS_R; k++) {
         const float *p = src + fb_m_index((unsigned)(clampi(y0 + k, 0, h - 1) * w + gx));
 #pragma unroll
         for (int c = 0; c < 5; c++) {
-            const float v = __ldg(p + c * FB_MS);
-            if (VACC) vd[c] += (double)v;
-            else ff_add(vh[c], vl[c], v);
+            vd[c] += (double)__ldg(p + c * FB_MS);
         }
     }
     // horizontal work item: 16 lanes per plane (14 segments of 8 outputs + 2 idle lanes), so that a
@@ -722,7 +654,7 @@ k_fb_blur_solve(const float *__restrict__ M, int h, int w, float2 *__restrict__ 
             yo++;
         }
 #pragma unroll
-        for (int c = 0; c < 5; c++) my_row[c * MS_VP] = VACC ? (float)vd[c] : __fadd_rn(vh[c], vl[c]);
+        for (int c = 0; c < 5; c++) my_row[c * MS_VP] = (float)vd[c];
         __syncthreads();
         if (hwork) {
             // p[k] = column 8s + k; output o of the segment sums columns 8s+o+1 .. 8s+o+15
@@ -763,34 +695,18 @@ k_fb_blur_solve(const float *__restrict__ M, int h, int w, float2 *__restrict__ 
             float2 o;
             o.x = __fmul_rn(__fmul_rn(nx, k2), idet);
             o.y = __fmul_rn(__fmul_rn(ny, k2), idet);
-            if (EPI == 0) {
-                if (write_flow) *fout = o;
-                // last iteration of level 0: the flow field itself is not needed any more, only
-                // sum |flow| (cartToPolar magnitude, complexity_metrics.py:342-343)
-                if (mag_sum) mag_acc += (double)sqrtf(__fadd_rn(__fmul_rn(o.x, o.x), __fmul_rn(o.y, o.y)));
-            } else {
-                const float *R0 = R + (size_t)pair * 5 * plane;
-                float m[5];
-                fb_matrix_at(R0, R0 + 5 * plane, plane, gxo, y, h, w, o, m);
-                float *dst = Mnext + (size_t)pair * fb_m_pair_floats(h, w) + fb_m_index((unsigned)(y * w + gxo));
-#pragma unroll
-                for (int c = 0; c < 5; c++) dst[c * FB_MS] = m[c];
-            }
+            if (write_flow) *fout = o;
+            // last iteration of level 0: the flow field itself is not needed any more, only
+            // sum |flow| (cartToPolar magnitude, complexity_metrics.py:342-343)
+            if (mag_sum) mag_acc += (double)sqrtf(__fadd_rn(__fmul_rn(o.x, o.x), __fmul_rn(o.y, o.y)));
         }
         fout += w;
         if (more) {
 #pragma unroll
-            for (int c = 0; c < 5; c++) {
-                if (VACC) {
-                    vd[c] = (vd[c] + (double)nin[c]) - (double)nout[c];
-                } else {
-                    ff_add(vh[c], vl[c], nin[c]);
-                    ff_add(vh[c], vl[c], -nout[c]);
-                }
-            }
+            for (int c = 0; c < 5; c++) vd[c] = (vd[c] + (double)nin[c]) - (double)nout[c];
         }
     }
-    if (EPI == 0 && mag_sum) {
+    if (mag_sum) {
         __shared__ double red[MS_W / 32];
         mag_acc = warp_sum(mag_acc);
         __syncthreads();
@@ -855,6 +771,10 @@ static void make_poly(PolyConst &pc)
     pc.ig11 = m[1][7]; pc.ig03 = m[0][9]; pc.ig33 = m[3][9]; pc.ig55 = m[5][11];
 }
 
+#ifdef VQA_AB
+#include "farneback_fused.cuh"
+#endif
+
 int run_farneback(vqa_ctx *c, const uint8_t *gray, int npairs, int h, int w, double *mag_sum, float *flow_out)
 {
     if (npairs <= 0) return VQA_OK;
@@ -872,12 +792,15 @@ int run_farneback(vqa_ctx *c, const uint8_t *gray, int npairs, int h, int w, dou
     VQA_BUF(c, R, float, "fb.R", full * 5 * nf);
     const size_t m_pair = fb_m_pair_floats(h, w);                  // super-chunked planar M (level 0 is the largest)
     VQA_BUF(c, M, float, "fb.M", m_pair * npairs);
-    static const int fuse_epi = getenv("VQA_FB_EPI") ? atoi(getenv("VQA_FB_EPI")) : 0;
-    static const int vacc = getenv("VQA_FB_VACC") ? atoi(getenv("VQA_FB_VACC")) : 1;
     VQA_BUF(c, flowA, float2, "fb.flowA", full * npairs);
     VQA_BUF(c, flowB, float2, "fb.flowB", full * npairs);
-    static const int mat_v4 = getenv("VQA_MAT_V4") ? atoi(getenv("VQA_MAT_V4")) : 1;
-    static const int pe_f32 = getenv("VQA_PE_F32") ? atoi(getenv("VQA_PE_F32")) : 1;
+#ifdef VQA_AB
+    // development build only (the product build reads no environment): fused iteration and strip-height knobs
+    const bool fused = getenv("VQA_FB_FUSED") && atoi(getenv("VQA_FB_FUSED"));
+    const int ms_h_cap = (getenv("VQA_MS_H") && atoi(getenv("VQA_MS_H")) >= 16) ? atoi(getenv("VQA_MS_H")) : MS_H;
+#else
+    constexpr int ms_h_cap = MS_H;
+#endif
     PolyConst pc;
     make_poly(pc);
     VQA_CUDA(c, cudaMemsetAsync(mag_sum, 0, sizeof(double) * (size_t)npairs, c->stream));
@@ -919,34 +842,27 @@ int run_farneback(vqa_ctx *c, const uint8_t *gray, int npairs, int h, int w, dou
         }
         VQA_BYTES(c, 24.0 * lw * lh * nf);
         const dim3 gE(cdiv(lw, PE_TW), cdiv(cdiv(lh, PE_TH), PE_STRIP), nf);
-        if (pe_f32) {
-            VQA_CUDA(c, cudaFuncSetAttribute(k_fb_polyexp<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, PE_SMEM));
-            VQA_LAUNCH(c, k_fb_polyexp<float>, gE, 256, PE_SMEM, I, lh, lw, pc, R);
-        } else {
-            VQA_CUDA(c, cudaFuncSetAttribute(k_fb_polyexp<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, PE_SMEM));
-            VQA_LAUNCH(c, k_fb_polyexp<double>, gE, 256, PE_SMEM, I, lh, lw, pc, R);
+        VQA_CUDA(c, cudaFuncSetAttribute(k_fb_polyexp, cudaFuncAttributeMaxDynamicSharedMemorySize, PE_SMEM));
+        VQA_LAUNCH(c, k_fb_polyexp, gE, 256, PE_SMEM, I, lh, lw, pc, R);
+#ifdef VQA_AB
+        if (fused) {
+            const int rc = run_fused_level(c, R, flow, prev, ph, pw, lh, lw, npairs, k == levels, k == 0, mag_sum, flow_out != nullptr);
+            if (rc != VQA_OK) return rc;
+            float2 *t = prev; prev = flow; flow = t;
+            ph = lh; pw = lw;
+            continue;
         }
-        const bool v4 = (lw & 3) == 0 && mat_v4;
-        const dim3 gV(cdiv(lw, 128), cdiv(lh, 8), npairs);
+#endif
+        // first UpdateMatrices of the level: zero flow at the coarsest level, else the coarser flow up-sampled on the fly
         if (k == levels) {
             VQA_BYTES(c, 60.0 * lw * lh * npairs);
-            if (v4) VQA_LAUNCH(c, k_fb_matrices_v4<2>, gV, 256, 0, R, flow, lh, lw, M, prev, ph, pw);
-            else VQA_LAUNCH(c, k_fb_matrices<2>, gP, 256, 0, R, flow, lh, lw, M, prev, ph, pw);
+            VQA_LAUNCH(c, k_fb_matrices<2>, gP, 256, 0, R, flow, lh, lw, M, prev, ph, pw);
         } else {
             VQA_BYTES(c, (60.0 * lw * lh + 8.0 * pw * ph) * npairs);
-            // the 4-pixel variant measured slower here (four serial bilinear up-samples per thread); the
-            // transposed variant up-samples one pixel per lane (VQA_MAT_T4U, A/B knob read per call)
-            const char *t4u_env = getenv("VQA_MAT_T4U");
-            if (v4 && (t4u_env ? atoi(t4u_env) != 0 : false))
-                VQA_LAUNCH(c, k_fb_matrices_t4<1>, gV, 256, 0, R, flow, lh, lw, M, prev, ph, pw);
-            else
-                VQA_LAUNCH(c, k_fb_matrices<1>, gP, 256, 0, R, flow, lh, lw, M, prev, ph, pw);
+            VQA_LAUNCH(c, k_fb_matrices<1>, gP, 256, 0, R, flow, lh, lw, M, prev, ph, pw);
         }
         // rows per block of the marching blur: long strips amortise the 15-row warm-up, but the small
         // pyramid levels need shorter strips to put >= ~3 waves of blocks on 148 SMs x 8 blocks
-        // VQA_MS_H: cap of the strip height (A/B knob, read per call; default MS_H)
-        const char *msh_env = getenv("VQA_MS_H");
-        const int ms_h_cap = (msh_env && atoi(msh_env) >= 16) ? atoi(msh_env) : MS_H;
         int rows_pb = ms_h_cap;
         {
             const long want = 3L * c->sm_count * 8, per_row_strip = (long)cdiv(lw, MS_OUT) * npairs;
@@ -955,36 +871,16 @@ int run_farneback(vqa_ctx *c, const uint8_t *gray, int npairs, int h, int w, dou
             if (rows_pb < 16) rows_pb = 16;
             if (rows_pb > ms_h_cap) rows_pb = ms_h_cap;
         }
-        float *Mcur = M, *Mnxt = nullptr;
-        if (fuse_epi) { VQA_BUF(c, M2, float, "fb.M2", m_pair * npairs); Mnxt = M2; }
         const dim3 gB(cdiv(lw, MS_OUT), cdiv(lh, rows_pb), npairs);
         for (int it = 0; it < 3; it++) {
             const bool last = (k == 0 && it == 2);
-            if (it < 2 && fuse_epi) {
-                // blur + solve + next UpdateMatrices: M 20 + R0 20 + R1 20 read, M' 20 written
-                VQA_BYTES(c, 80.0 * lw * lh * npairs);
-                VQA_LAUNCH(c, (k_fb_blur_solve<1, 0>), gB, MS_W, 0, Mcur, lh, lw, flow, rows_pb, (double *)nullptr, 0, R, Mnxt);
-                float *tm = Mcur; Mcur = Mnxt; Mnxt = tm;
-                continue;
-            }
             VQA_BYTES(c, 28.0 * lw * lh * npairs);
-            if (vacc)
-                VQA_LAUNCH(c, (k_fb_blur_solve<0, 1>), gB, MS_W, 0, Mcur, lh, lw, flow, rows_pb,
-                           last ? mag_sum : (double *)nullptr, (!last || flow_out) ? 1 : 0, (const float *)nullptr, (float *)nullptr);
-            else
-                VQA_LAUNCH(c, (k_fb_blur_solve<0, 0>), gB, MS_W, 0, Mcur, lh, lw, flow, rows_pb,
-                           last ? mag_sum : (double *)nullptr, (!last || flow_out) ? 1 : 0, (const float *)nullptr, (float *)nullptr);
+            VQA_LAUNCH(c, k_fb_blur_solve, gB, MS_W, 0, M, lh, lw, flow, rows_pb, last ? mag_sum : (double *)nullptr,
+                       (!last || flow_out) ? 1 : 0);
             if (it < 2) {
                 VQA_BYTES(c, 68.0 * lw * lh * npairs);
-                const char *t4_env = getenv("VQA_MAT_T4");           // A/B knob, read per call
-                const bool mat_t4 = t4_env ? atoi(t4_env) != 0 : true;    // measured 3-5 % faster than v4<0>, same bits
-                if ((lw & 3) == 0 && mat_v4 && mat_t4) {
-                    VQA_LAUNCH(c, k_fb_matrices_t4<0>, dim3(cdiv(lw, 128), cdiv(lh, 8), npairs), 256, 0, R, flow, lh, lw, Mcur, prev, ph, pw);
-                } else if ((lw & 3) == 0 && mat_v4) {
-                    VQA_LAUNCH(c, k_fb_matrices_v4<0>, dim3(cdiv(lw, 128), cdiv(lh, 8), npairs), 256, 0, R, flow, lh, lw, Mcur, prev, ph, pw);
-                } else {
-                    VQA_LAUNCH(c, k_fb_matrices<0>, gP, 256, 0, R, flow, lh, lw, Mcur, prev, ph, pw);
-                }
+                if ((lw & 3) == 0) VQA_LAUNCH(c, k_fb_matrices_t4, dim3(cdiv(lw, 128), cdiv(lh, 8), npairs), 256, 0, R, flow, lh, lw, M);
+                else VQA_LAUNCH(c, k_fb_matrices<0>, gP, 256, 0, R, flow, lh, lw, M, prev, ph, pw);
             }
         }
         float2 *t = prev; prev = flow; flow = t;
