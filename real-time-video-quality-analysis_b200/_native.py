@@ -208,12 +208,17 @@ class Context:
             import torch
             if frames.dtype != torch.uint8 or frames.dim() != 4 or frames.shape[-1] != 3:
                 raise TypeError("expected a (n,h,w,3) uint8 CUDA tensor")
+            if frames.device.index != self.device:
+                raise TypeError("frames live on %s, this context drives cuda:%d" % (frames.device, self.device))
             frames = frames.contiguous()
             torch.cuda.current_stream(frames.device).synchronize()
             n, h, w, _ = frames.shape
             ptr, on_dev, stride = frames.data_ptr(), 1, h * w * 3
             hptr = None
             if halo is not None:
+                if not (_is_torch_tensor(halo) and halo.is_cuda and halo.device == frames.device and halo.dtype == torch.uint8
+                        and tuple(halo.shape) == (h, w, 3)):
+                    raise TypeError("halo must be a (h,w,3) uint8 tensor on the frames' device")
                 halo = halo.contiguous()
                 hptr = halo.data_ptr()
             keep = (frames, halo)

@@ -117,17 +117,22 @@ def read_frame_pairs(video_path, frame_interval=10):
 
 # --------------------------------------------------------------------------- series helpers
 def smooth_data(data, alpha=0.8):
-    """pd.Series(data).ewm(alpha=alpha).mean().to_numpy() (reference :114-125, adjust=True),
+    """pd.Series(data).ewm(alpha=alpha).mean().to_numpy() (reference :114-125; adjust=True, ignore_na=False),
     float64.  O(T) scalar recurrence on the host; the clip-level mean of the smoothed series
-    is reduced on the device (``Context.ewm_partial``)."""
+    is reduced on the device (``Context.ewm_partial``).  NaN observations follow pandas: they are left out of
+    both sums while the weights of the older terms keep decaying, the previous smoothed value is carried forward,
+    and positions before the first valid observation stay NaN."""
     x = np.asarray(list(data) if not isinstance(data, np.ndarray) else data, dtype=np.float64)
     out = np.empty_like(x)
     num = den = 0.0
     beta = 1.0 - alpha
     for t in range(x.shape[0]):
-        num = num * beta + x[t]
-        den = den * beta + 1.0
-        out[t] = num / den
+        num *= beta
+        den *= beta
+        if x[t] == x[t]:
+            num += x[t]
+            den += 1.0
+        out[t] = num / den if den > 0.0 else np.nan
     return out
 
 
@@ -136,6 +141,10 @@ def _smoothed_mean(series, alpha, empty=float("nan")):
     series = np.asarray(series, dtype=np.float64)
     if series.size == 0:
         return np.float64(empty)
+    if np.isnan(series).any():
+        # the closed-form weights of the device reduction assume every term is present; with missing observations
+        # the reference's value is np.mean of the pandas-smoothed series (NaN iff the series STARTS with NaN)
+        return np.float64(np.mean(smooth_data(series, alpha)))
     return np.float64(N.get_context().ewm_partial(series, 0, series.size, alpha))
 
 
@@ -324,6 +333,12 @@ def stream_clip_metrics(video_path, resize_width, resize_height, frame_interval=
     for chunk in src:
         if ctx is None:
             ctx = N.get_context()
+        if halo is not None and halo.shape != chunk.shape[1:]:
+            # the source flushes a partial chunk when the decoder changes the frame size; the pair across that
+            # boundary has no optical flow (cv2.calcOpticalFlowFarneback rejects it in the reference as well)
+            raise ValueError("frame size changes mid-stream (%dx%d -> %dx%d) after %d sampled frames: the pair metrics "
+                             "are undefined across the change" % (halo.shape[1], halo.shape[0], chunk.shape[2],
+                                                                  chunk.shape[1], sum(len(p) for p in parts)))
         parts.append(ctx.complexity_frames(chunk, resize_width, resize_height, mask, halo=halo,
                                            orb_size=_orb_size(orb_size)))
         halo = chunk[-1]

@@ -52,7 +52,9 @@ def thread_safe_update_csv(metrics, csv_file='video_quality_data.csv'):
                 w = csv.writer(f, lineterminator='\n')
                 if not file_exists:
                     w.writerow(list(metrics.keys()))
-                w.writerow(["" if v is None else (repr(float(v)) if isinstance(v, (float, np.floating)) else v)
+                # DataFrame.to_csv writes missing values (None / NaN) as empty fields
+                w.writerow(["" if v is None or (isinstance(v, (float, np.floating)) and np.isnan(v))
+                            else (repr(float(v)) if isinstance(v, (float, np.floating)) else v)
                             for v in metrics.values()])
         except IOError as e:
             logger.error("Failed to write to CSV file: %s", e)
@@ -180,31 +182,75 @@ def _probe_size(path):
     return int(w), int(h)
 
 
-def _decode_yuv420(path, w, h, max_frames=None):
-    """Decode to planar yuv420p with the ffmpeg executable (container decode is out of scope)."""
+FR_CHUNK_FRAMES = 64          # frames per PSNR/SSIM device call: host memory stays O(chunk), like ffmpeg's own O(1) filters
+_YUV420_8BIT = ('yuv420p', 'yuvj420p', 'nv12', 'nv21')
+
+
+def _probe_pix_fmt(path):
+    """pix_fmt of the first video stream, or None when ffprobe does not report one."""
+    cmd = ['ffprobe', '-v', 'error', '-select_streams', 'v:0', '-print_format', 'json', '-show_entries',
+           'stream=pix_fmt', path]
+    try:
+        out = subprocess.run(cmd, check=True, stdout=subprocess.PIPE).stdout
+        return json.loads(out)['streams'][0].get('pix_fmt')
+    except Exception:
+        return None
+
+
+def _yuv420_chunks(path, w, h, chunk):
+    """Decode to planar yuv420p with the ffmpeg executable (container decode is out of scope) and yield
+    (Y [n,h,w], U, V [n,ceil(h/2),ceil(w/2)]) stacks of at most ``chunk`` frames read from the pipe as they come."""
+    cw, ch = (w + 1) // 2, (h + 1) // 2
+    ysz, csz = w * h, cw * ch
+    fsz = ysz + 2 * csz
     cmd = ['ffmpeg', '-v', 'error', '-i', path, '-f', 'rawvideo', '-pix_fmt', 'yuv420p', '-']
-    raw = subprocess.run(cmd, check=True, stdout=subprocess.PIPE).stdout
-    fsz = w * h * 3 // 2
-    n = len(raw) // fsz
-    if max_frames:
-        n = min(n, max_frames)
-    a = np.frombuffer(raw, np.uint8, n * fsz).reshape(n, fsz)
-    y = np.ascontiguousarray(a[:, :w * h]).reshape(n, h, w)
-    u = np.ascontiguousarray(a[:, w * h:w * h * 5 // 4]).reshape(n, h // 2, w // 2)
-    v = np.ascontiguousarray(a[:, w * h * 5 // 4:]).reshape(n, h // 2, w // 2)
-    return y, u, v
+    proc = subprocess.Popen(cmd, stdout=subprocess.PIPE)
+    try:
+        while True:
+            parts, need = [], fsz * chunk
+            while need > 0:
+                b = proc.stdout.read(need)
+                if not b:
+                    break
+                parts.append(b)
+                need -= len(b)
+            raw = b''.join(parts)
+            n = len(raw) // fsz
+            if n == 0:
+                break
+            a = np.frombuffer(raw, np.uint8, n * fsz).reshape(n, fsz)
+            yield (np.ascontiguousarray(a[:, :ysz]).reshape(n, h, w),
+                   np.ascontiguousarray(a[:, ysz:ysz + csz]).reshape(n, ch, cw),
+                   np.ascontiguousarray(a[:, ysz + csz:]).reshape(n, ch, cw))
+            if need > 0:
+                break
+    finally:
+        proc.stdout.close()
+        rc = proc.wait()
+    if rc != 0:
+        raise subprocess.CalledProcessError(rc, cmd)
 
 
 def run_ffmpeg_metrics(reference_video, distorted_video, psnr_log, ssim_log, vmaf_log, vmaf_model_path=None):
     """PSNR + SSIM on the GPU, VMAF through FFmpeg/libvmaf (reference :270-297).  Produces the
-    same three files the reference's single ffmpeg invocation produces.  Decode failures and a
-    failing libvmaf run are logged and re-raised like the reference's CalledProcessError path."""
+    same three files the reference's single ffmpeg invocation produces.  The two decodes are read from
+    their pipes in bounded chunks (``FR_CHUNK_FRAMES``) and scored chunk by chunk.  FFmpeg's psnr/ssim
+    filters work in the main input's own pixel format; this path covers 8-bit 4:2:0 and says so for
+    anything else instead of scoring a silently converted picture.  Decode failures and a failing
+    libvmaf run are logged and re-raised like the reference's CalledProcessError path."""
     try:
         w, h = _probe_size(distorted_video)
-        main = _decode_yuv420(distorted_video, w, h)
-        ref = _decode_yuv420(reference_video, w, h)
-        n = min(len(main[0]), len(ref[0]))
-        rows = psnr_ssim_frames([p[:n] for p in main], [p[:n] for p in ref])
+        fmt = _probe_pix_fmt(distorted_video)
+        if fmt is not None and fmt not in _YUV420_8BIT:
+            raise NotImplementedError(f"PSNR/SSIM on the device covers 8-bit 4:2:0 video; {distorted_video} is {fmt}")
+        parts = []
+        for main, ref in zip(_yuv420_chunks(distorted_video, w, h, FR_CHUNK_FRAMES),
+                             _yuv420_chunks(reference_video, w, h, FR_CHUNK_FRAMES)):
+            n = min(len(main[0]), len(ref[0]))
+            parts.append(psnr_ssim_frames([p[:n] for p in main], [p[:n] for p in ref]))
+            if len(main[0]) != len(ref[0]):
+                break
+        rows = np.concatenate(parts) if parts else np.zeros(0, dtype=N.FR_DTYPE)
         write_ffmpeg_stats(rows, psnr_log, ssim_log)
         if vmaf_model_path and os.path.isfile(vmaf_model_path):
             flt = f"[0:v][1:v]libvmaf=model_path={vmaf_model_path}:log_path={vmaf_log}:log_fmt=json"

@@ -60,8 +60,11 @@ def config1_sampled_frames(synth, n=300, h=1080, w=1920, interval=10, seed=0):
 FAKE_TOOL = r'''#!%(python)s
 """Test double of the ffmpeg / ffprobe command lines the reference issues (tests/helpers.py)."""
 import json, re, sys
+import os
 import cv2
 import numpy as np
+
+FAKE_PIX_FMT = os.environ.get("FAKE_FFPROBE_PIX_FMT", "yuv420p")
 
 
 def decode(path):
@@ -91,7 +94,8 @@ def main(argv):
     a = argv[1:]
     if tool == "ffprobe":
         f = decode(a[-1])[0]
-        print(json.dumps({"streams": [{"width": f.shape[1], "height": f.shape[0], "avg_frame_rate": "30/1", "bit_rate": "1234567"}]}))
+        print(json.dumps({"streams": [{"width": f.shape[1], "height": f.shape[0], "avg_frame_rate": "30/1", "bit_rate": "1234567",
+                                       "pix_fmt": FAKE_PIX_FMT}]}))
     elif "-c:v" in a:
         encode(a[a.index("-i") + 1], a[-1])
     elif "rawvideo" in a:

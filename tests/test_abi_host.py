@@ -155,6 +155,27 @@ def test_csv_contract(vqa, tmp_path):
     lines = csv_file.read_text().splitlines()
     assert len(lines) == 3 and lines[0].split(",") == vp.CSV_COLUMNS          # README.md:71 header, written once
     assert lines[1].startswith("4486,1920x1080,30.0,23,50.78,0.994884,95.837165,1.0,2.0")
+    # a missing metric is an empty field, as DataFrame.to_csv writes it (reference :59-65)
+    vp.thread_safe_update_csv({**row, 'VMAF': float("nan"), 'PSNR': None}, str(csv_file))
+    assert csv_file.read_text().splitlines()[3].startswith("4486,1920x1080,30.0,23,,0.994884,,1.0")
+
+
+def test_smooth_data_follows_pandas_on_missing_observations(vqa):
+    """pd.Series(x).ewm(alpha).mean() with NaN terms (reference :114-125): skipped, weights keep decaying, the value
+    is carried forward, leading NaNs stay NaN; np.mean of it is what calculate_average_scene_complexity returns."""
+    pd = pytest.importorskip("pandas")
+    from rtvqa_b200 import complexity_metrics as cm
+    rng = np.random.default_rng(5)
+    for trial in range(12):
+        x = rng.normal(size=33)
+        x[rng.integers(0, 33, size=trial % 6)] = np.nan
+        if trial % 4 == 0:
+            x[0] = np.nan
+        want = pd.Series(x).ewm(alpha=0.8).mean().to_numpy()
+        np.testing.assert_allclose(cm.smooth_data(x, 0.8), want, rtol=1e-13, atol=0, equal_nan=True)
+        if np.isnan(x).any():                                   # host path; NaN-free series go through the device reduction
+            got = cm._smoothed_mean(x, 0.8)
+            assert (np.isnan(got) and np.isnan(np.mean(want))) or got == pytest.approx(np.mean(want), rel=1e-13)
 
 
 def test_stats_files_round_trip_through_the_reference_regexes(vqa, tmp_path):

@@ -94,6 +94,9 @@ def test_cli_flow_with_oracle_kernels(vqa, cli, monkeypatch):
         return RP.average_scene_complexity(np.stack(frames), rw, rh, frame_interval=frame_interval)
 
     monkeypatch.setattr(vp, "psnr_ssim_frames", fake_fr)
+    monkeypatch.setattr(vp, "FR_CHUNK_FRAMES", 4)                            # several bounded reads of the two decode pipes
+    chunks = list(vp._yuv420_chunks(cli["src"], 128, 96, chunk=4))
+    assert [len(c[0]) for c in chunks] == [4] * (len(enc_frames) // 4) + ([len(enc_frames) % 4] if len(enc_frames) % 4 else [])
     monkeypatch.setattr(vp, "calculate_average_scene_complexity", fake_complexity)
     cfg_file = cli["tmp"] / "config.json"
     cfg_file.write_text(__import__("json").dumps(CFG))
@@ -102,6 +105,10 @@ def test_cli_flow_with_oracle_kernels(vqa, cli, monkeypatch):
     _check_csv(cli, fr, vals, rtol=1e-12)
     with pytest.raises(FileNotFoundError):
         vp.process_video_and_extract_metrics(str(cli["tmp"] / "missing.mp4"), CFG)
+    # anything but 8-bit 4:2:0 is refused rather than scored after a silent conversion
+    monkeypatch.setenv("FAKE_FFPROBE_PIX_FMT", "yuv444p10le")
+    with pytest.raises(NotImplementedError):
+        vp.run_ffmpeg_metrics(cli["src"], cli["src"], str(cli["tmp"] / "p.log"), str(cli["tmp"] / "s.log"), str(cli["tmp"] / "v.json"))
 
 
 @pytest.mark.gpu
