@@ -253,6 +253,102 @@ k_fb_pyramid3(const uint8_t *__restrict__ gray, int H, int W, int lh, int lw, fl
     }
 }
 
+// Pyramid levels 2 and 3 of a frame whose sides divide by 8 (exact 4x / 8x decimation; Gaussian radius 4 / 9): the same
+// arithmetic as k_fb_pyramid in mode 2 -- horizontal Gaussian at the two source columns S*x + S/2 - 1, + 0 / + 1 each
+// output samples (bilinear weight exactly 0.5), vertical Gaussian at the two source rows, combine -- restructured for
+// instruction issue (the generic kernel spent 1.4 + 1.5 ms per 300 frames on two levels that hold 8 % of the pixels:
+// byte loads from shared memory, a runtime division per loaded word, 20 % issue utilisation).  Here a horizontal work
+// item produces BOTH columns of an output from one aligned 24- / 12-byte read of the uint8 tile (the two 19- / 9-tap
+// windows overlap in all but one byte), rows are loaded with one 2-D thread mapping, and a vertical work item reads
+// float2 pairs.  Tile: 32 x TO outputs per block.
+template <int S, int R, int TO>
+__global__ void __launch_bounds__(256)
+k_fb_pyramid_dec(const uint8_t *__restrict__ gray, int H, int W, int lh, int lw, GaussTaps taps, float *__restrict__ I)
+{
+    constexpr int A = S == 8 ? 8 : 4;                   // tile column 0 = source column S*tx0 - A (keeps the work-item reads aligned)
+    constexpr int NB = S == 8 ? 24 : 12;                // bytes a horizontal work item reads: tile columns S*x .. S*x + NB - 1
+    constexpr int C0 = A + S / 2 - 1;                   // centre of the first window inside those bytes (11 / 5); second: C0 + 1
+    constexpr int WB = 32 * S + NB - S, WP = (WB + 15) & ~15;       // tile width in bytes (272 / 136) and its pitch
+    constexpr int RH = S * (TO - 1) + 2 * R + 2;        // source rows S*ty0 + S/2 - 1 - R .. (140 / 134)
+    extern __shared__ __align__(16) uint8_t pd_smem[];
+    uint8_t *src = pd_smem;                                             // [RH][WP]
+    float2 *hb = reinterpret_cast<float2 *>(pd_smem + RH * WP);         // [RH][32]: both blurred columns of output x
+    const int frame = blockIdx.z, tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+    const uint8_t *img = gray + (size_t)frame * H * W;
+    const int tx0 = blockIdx.x * 32, ty0 = blockIdx.y * TO;
+    const int xs0 = S * tx0 - A, ys0 = S * ty0 + S / 2 - 1 - R;
+    float tk[R + 1];
+#pragma unroll
+    for (int k = 0; k <= R; k++) tk[k] = taps.k[R + k];
+    for (int ry = wrp; ry < RH; ry += 8) {
+        const uint8_t *g = img + (size_t)reflect101(ys0 + ry, H) * W;
+        uint32_t *d = reinterpret_cast<uint32_t *>(src + ry * WP);
+        for (int q = lane; q < WP / 4; q += 32) {
+            const int gx = xs0 + 4 * q;                                  // W % 4 == 0 (S divides W): words never straddle the border
+            uint32_t v;
+            if (gx >= 0 && gx + 4 <= W) v = __ldg(reinterpret_cast<const uint32_t *>(g + gx));
+            else {
+                v = 0;
+#pragma unroll
+                for (int b = 0; b < 4; b++) v |= (uint32_t)__ldg(g + reflect101(gx + b, W)) << (8 * b);
+            }
+            d[q] = v;
+        }
+    }
+    __syncthreads();
+    for (int ry = wrp; ry < RH; ry += 8) {
+        uint32_t wv[NB / 4];
+        if (S == 8) {
+            const uint2 *p = reinterpret_cast<const uint2 *>(src + ry * WP + 8 * lane);
+#pragma unroll
+            for (int j = 0; j < 3; j++) { const uint2 v = p[j]; wv[2 * j] = v.x; wv[2 * j + 1] = v.y; }
+        } else {
+            const uint32_t *p = reinterpret_cast<const uint32_t *>(src + ry * WP + 4 * lane);
+#pragma unroll
+            for (int j = 0; j < 3; j++) wv[j] = p[j];
+        }
+#define PD_B(i) ((int)((wv[(i) >> 2] >> (8 * ((i) & 3))) & 255u))
+        float s0 = tk[0] * (float)PD_B(C0), s1 = tk[0] * (float)PD_B(C0 + 1);
+#pragma unroll
+        for (int k = 1; k <= R; k++) {
+            s0 += tk[k] * (float)(PD_B(C0 - k) + PD_B(C0 + k));
+            s1 += tk[k] * (float)(PD_B(C0 + 1 - k) + PD_B(C0 + 1 + k));
+        }
+#undef PD_B
+        hb[ry * 32 + lane] = make_float2(s0, s1);
+    }
+    __syncthreads();
+    const int x = tx0 + lane;
+    for (int oy = wrp; oy < TO; oy += 8) {
+        const int y = ty0 + oy;
+        if (y >= lh || x >= lw) continue;
+        const float2 *c = hb + (S * oy + R) * 32 + lane;               // centre row of the first vertical window; second: + 1 row
+        const float2 c0 = c[0], c1 = c[32];
+        float v00 = tk[0] * c0.x, v01 = tk[0] * c0.y, v10 = tk[0] * c1.x, v11 = tk[0] * c1.y;
+#pragma unroll
+        for (int k = 1; k <= R; k++) {
+            const float2 a0 = c[-k * 32], b0 = c[k * 32], a1 = c[(1 - k) * 32], b1 = c[(1 + k) * 32];
+            v00 += tk[k] * (a0.x + b0.x);
+            v01 += tk[k] * (a0.y + b0.y);
+            v10 += tk[k] * (a1.x + b1.x);
+            v11 += tk[k] * (a1.y + b1.y);
+        }
+        const float t0 = __fadd_rn(__fmul_rn(v00, 0.5f), __fmul_rn(v01, 0.5f));
+        const float t1 = __fadd_rn(__fmul_rn(v10, 0.5f), __fmul_rn(v11, 0.5f));
+        I[(size_t)frame * lh * lw + (size_t)y * lw + x] = __fadd_rn(__fmul_rn(t0, 0.5f), __fmul_rn(t1, 0.5f));
+    }
+}
+
+template <int S, int R, int TO>
+static int launch_pyramid_dec(vqa_ctx *c, const uint8_t *gray, int h, int w, int lh, int lw, int nf, const GaussTaps &taps, float *I)
+{
+    constexpr int NB = S == 8 ? 24 : 12, WP = ((32 * S + NB - S) + 15) & ~15, RH = S * (TO - 1) + 2 * R + 2;
+    constexpr int smem = RH * WP + RH * 32 * (int)sizeof(float2);
+    VQA_CUDA(c, cudaFuncSetAttribute(k_fb_pyramid_dec<S, R, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    VQA_LAUNCH(c, (k_fb_pyramid_dec<S, R, TO>), dim3(cdiv(lw, 32), cdiv(lh, TO), nf), 256, smem, gray, h, w, lh, lw, taps, I);
+    return VQA_OK;
+}
+
 constexpr int PE_TW = 64, PE_TH = 32, PE_R = 5;
 constexpr int PE_P = 76;                         // tile pitch (64 + 2*5 = 74, padded so rows stay 16-byte aligned)
 
@@ -834,6 +930,10 @@ int run_farneback(vqa_ctx *c, const uint8_t *gray, int npairs, int h, int w, dou
                 VQA_LAUNCH(c, k_fb_pyramid3<0>, dim3(cdiv(w, 128), cdiv(h, 8), nf), 256, 0, gray, h, w, lh, lw, taps.k[0], taps.k[1], I);
             } else if (ksz == 3 && mode == 1) {
                 VQA_LAUNCH(c, k_fb_pyramid3<1>, dim3(cdiv(w, 128), cdiv(h, 16), nf), 256, 0, gray, h, w, lh, lw, taps.k[0], taps.k[1], I);
+            } else if (ksz == 9 && w == 4 * lw && h == 4 * lh) {
+                if (int rc = launch_pyramid_dec<4, 4, 32>(c, gray, h, w, lh, lw, nf, taps, I)) return rc;
+            } else if (ksz == 19 && w == 8 * lw && h == 8 * lh) {
+                if (int rc = launch_pyramid_dec<8, 9, 16>(c, gray, h, w, lh, lw, nf, taps, I)) return rc;
             } else {
                 if (ksz == 19) VQA_LAUNCH(c, k_fb_pyramid<9>, gF, PY_TW * PY_TH, smem, gray, h, w, lh, lw, mode, taps, I, rwp);
                 else if (ksz == 9) VQA_LAUNCH(c, k_fb_pyramid<4>, gF, PY_TW * PY_TH, smem, gray, h, w, lh, lw, mode, taps, I, rwp);
