@@ -393,6 +393,7 @@ int complexity_body(vqa_ctx *c, const uint8_t *bgr, int n, int h, int w, size_t 
     VQA_BUF(c, d_mag, double, "res.mag", n);
     VQA_BUF(c, d_orb, int, "res.orb", n);
     VQA_BUF(c, d_hist, uint32_t, "ing.hist", (size_t)CH * 1024);
+    VQA_BUF(c, d_psum, unsigned long long, "ing.psum", CH);        // sum of the gray pixels per frame (moments of the gray histogram)
     VQA_BUF(c, G, uint8_t, "ing.gray", HW * (CH + 1));
     uint8_t *gs = nullptr, *xs = nullptr;
     if (!identity) {
@@ -554,11 +555,14 @@ int complexity_body(vqa_ctx *c, const uint8_t *bgr, int n, int h, int w, size_t 
             src = yuv ? conv : in[ci % 3];
             stride = FB;
         }
+        uint8_t *Gc = G + HW;                       // slots 1..m
+        // planes of this chunk (staged or the caller's device stacks); fused = the native-resolution analysis reads them
+        // directly (gray + histograms in one pass, ORB's 100 taps converted on the fly), else BGR frames are derived first
+        const uint8_t *mp[3] = {nullptr, nullptr, nullptr}, *rp[3] = {nullptr, nullptr, nullptr};
+        int pst[3] = {0, 0, 0};
+        size_t pfs[3] = {0, 0, 0};
+        bool fused = false;
         if (yuv) {
-            // planes of this chunk (staged or the caller's device stacks) -> BGR frames; PSNR/SSIM of the same planes
-            const uint8_t *mp[3], *rp[3];
-            int pst[3];
-            size_t pfs[3];
             for (int p = 0; p < 3; p++) {
                 if (on_device) {
                     pst[p] = yuv->stride[p];
@@ -572,21 +576,30 @@ int complexity_body(vqa_ctx *c, const uint8_t *bgr, int n, int h, int w, size_t 
                     rp[p] = want_fr ? slot_plane(ci % 3, 3 + p) : nullptr;
                 }
             }
-            stage_begin(c, "ingest");
-            if ((rc = run_yuv420_to_bgr(c, mp, pst, pfs, m, h, w, conv))) return rc;
-            stage_end(c, "ingest");
+            fused = identity && need_full_gray && (!orb_general || orb_native) && yuv420_gray_hist_ok(mp, pst, pfs, h, w, Gc);
+            if (!fused) {
+                stage_begin(c, "ingest");
+                if ((rc = run_yuv420_to_bgr(c, mp, pst, pfs, m, h, w, conv))) return rc;
+                stage_end(c, "ingest");
+            }
             if (want_fr) {
                 stage_begin(c, "frscore");
                 if ((rc = run_psnr_ssim_planes(c, mp, rp, m, yuv->ph, yuv->pw, pst, pfs, d_sse + s, d_ssim + s, n))) return rc;
                 stage_end(c, "frscore");
             }
         }
-        uint8_t *Gc = G + HW;                       // slots 1..m
         // ---- ingest
         stage_begin(c, "ingest");
+        // with the gray histogram of the very image the DCT consumes, sum x (DCT mean) and sum x^2 (Parseval check) are
+        // its moments: two passes over the frame saved
+        const bool moments = identity && need_full_gray && want_hist && want_dct;
         if (identity) {
-            if (need_full_gray)
-                if ((rc = run_gray_hist(c, src, m, h, w, stride, Gc, want_hist ? d_hist : nullptr))) return rc;
+            if (need_full_gray) {
+                if (fused) rc = run_yuv420_gray_hist(c, mp, pst, pfs, m, h, w, Gc, want_hist ? d_hist : nullptr);
+                else rc = run_gray_hist(c, src, m, h, w, stride, Gc, want_hist ? d_hist : nullptr);
+                if (rc) return rc;
+            }
+            if (moments) if ((rc = run_hist_moments(c, d_hist, m, d_psum, d_sq + s))) return rc;
         } else {
             if (need_full_gray) if ((rc = run_gray_hist(c, src, m, h, w, stride, Gc, nullptr))) return rc;
             if (want_hist || want_edge)
@@ -613,7 +626,9 @@ int complexity_body(vqa_ctx *c, const uint8_t *bgr, int n, int h, int w, size_t 
             if (want_orb) {
                 stage_begin(c, "orb");
                 if (!orb_general) {
-                    if ((rc = run_orb64(c, src, m, h, w, stride, d_orb + s))) return rc;
+                    if (fused) rc = run_orb64_yuv(c, mp, pst, pfs, m, h, w, d_orb + s);
+                    else rc = run_orb64(c, src, m, h, w, stride, d_orb + s);
+                    if (rc) return rc;
                 } else if (orb_native) {
                     if ((rc = run_orb_general(c, Gc, m, h, w, HW, w, nullptr, d_orb + s, nullptr, nullptr, 0))) return rc;
                 } else {
@@ -627,8 +642,8 @@ int complexity_body(vqa_ctx *c, const uint8_t *bgr, int n, int h, int w, size_t 
             if (want_dct) {
                 stage_begin(c, "dct");
                 const uint8_t *X = identity ? Gc : xs + RR;
-                if ((rc = run_dct(c, X, m, rh, rw, cfg->dct_impl, Cbuf + RR, d_energy + s))) return rc;
-                if ((rc = run_sq_sum(c, X, m, (long)RR, d_sq + s))) return rc;
+                if ((rc = run_dct(c, X, m, rh, rw, cfg->dct_impl, Cbuf + RR, d_energy + s, moments ? d_psum : nullptr))) return rc;
+                if (!moments) if ((rc = run_sq_sum(c, X, m, (long)RR, d_sq + s))) return rc;
                 if (want_tdct) {
                     const int first = has_prev ? 0 : 1;
                     if (m - first > 0)

@@ -171,11 +171,12 @@ static int dct_simt(vqa_ctx *c, const uint8_t *x, int n, int h, int w, float *co
     return VQA_OK;
 }
 
-int run_dct(vqa_ctx *c, const uint8_t *x, int n, int h, int w, int impl, float *coef, double *energy)
+int run_dct(vqa_ctx *c, const uint8_t *x, int n, int h, int w, int impl, float *coef, double *energy,
+            const unsigned long long *pixel_sums)
 {
     VQA_CUDA(c, cudaMemsetAsync(energy, 0, sizeof(double) * (size_t)n, c->stream));
     if (impl == 1) return dct_simt(c, x, n, h, w, coef, energy);
-    return run_dct_umma(c, x, n, h, w, coef, energy);
+    return run_dct_umma(c, x, n, h, w, coef, energy, pixel_sums);
 }
 
 int run_abs_diff_sum(vqa_ctx *c, const float *a, const float *b, int n, long per_frame, size_t stride_a,

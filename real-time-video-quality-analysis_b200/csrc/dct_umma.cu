@@ -460,7 +460,8 @@ static int make_map(vqa_ctx *c, UmmaState *s, CUtensorMap *m, const void *base, 
 
 static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
-int run_dct_umma(vqa_ctx *c, const uint8_t *x, int n, int h, int w, float *coef, double *energy)
+int run_dct_umma(vqa_ctx *c, const uint8_t *x, int n, int h, int w, float *coef, double *energy,
+                 const unsigned long long *pixel_sums)
 {
     // N tile per GEMM (measured, 48 x 1080p): GEMM 1 with BN = 256 (3 stages of 64 KB) runs at
     // 1356 TFLOP/s issued vs 1110 with BN = 128; GEMM 2 with BN = 256 has room for 2 stages only
@@ -488,14 +489,18 @@ int run_dct_umma(vqa_ctx *c, const uint8_t *x, int n, int h, int w, float *coef,
         VQA_CUDA(c, cudaFuncSetAttribute(k_dct_umma<BN2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<BN2, 2>::SMEM_BYTES));
         s->attr_set = true;
     }
-    VQA_BUF(c, sums, unsigned long long, "umma.sums", n);
-    VQA_CUDA(c, cudaMemsetAsync(sums, 0, sizeof(unsigned long long) * (size_t)n, c->stream));
+    VQA_BUF(c, sums_buf, unsigned long long, "umma.sums", n);
+    const unsigned long long *sums = pixel_sums;            // the caller may already know them (gray histogram moments)
     int bpf = cdiv((long)h * w, 256 * 8);
     if (bpf < 1) bpf = 1;
-    int bps = cdiv((long)h * w, 256 * 16 * 4);
-    if (bps < 1) bps = 1;
-    VQA_BYTES(c, 1.0 * h * w * n);
-    VQA_LAUNCH(c, k_frame_sum, dim3(bps, n), 256, 0, x, (long)h * w, sums);
+    if (!sums) {
+        VQA_CUDA(c, cudaMemsetAsync(sums_buf, 0, sizeof(unsigned long long) * (size_t)n, c->stream));
+        int bps = cdiv((long)h * w, 256 * 16 * 4);
+        if (bps < 1) bps = 1;
+        VQA_BYTES(c, 1.0 * h * w * n);
+        VQA_LAUNCH(c, k_frame_sum, dim3(bps, n), 256, 0, x, (long)h * w, sums_buf);
+        sums = sums_buf;
+    }
     VQA_BYTES(c, 3.0 * h * w * n);
     VQA_LAUNCH(c, k_u8_to_bf16, dim3(bpf, n), 256, 0, x, h, w, ldw, sums, X);
 

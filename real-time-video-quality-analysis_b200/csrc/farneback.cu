@@ -280,21 +280,28 @@ k_fb_pyramid_dec(const uint8_t *__restrict__ gray, int H, int W, int lh, int lw,
     float tk[R + 1];
 #pragma unroll
     for (int k = 0; k <= R; k++) tk[k] = taps.k[R + k];
+    // source columns at and beyond W + R + 1 feed no output that exists (the ragged last tile of a row)
+    const int q_end = min(WP / 4, (W + R + 1 - xs0 + 3) >> 2);
     for (int ry = wrp; ry < RH; ry += 8) {
         const uint8_t *g = img + (size_t)reflect101(ys0 + ry, H) * W;
         uint32_t *d = reinterpret_cast<uint32_t *>(src + ry * WP);
-        for (int q = lane; q < WP / 4; q += 32) {
+        for (int q = lane; q < q_end; q += 32) {
             const int gx = xs0 + 4 * q;                                  // W % 4 == 0 (S divides W): words never straddle the border
-            uint32_t v;
-            if (gx >= 0 && gx + 4 <= W) v = __ldg(reinterpret_cast<const uint32_t *>(g + gx));
-            else {
-                v = 0;
+            if (gx >= 0 && gx + 4 <= W) {
+                // asynchronous copy: the ~40 words a thread fetches are all in flight at once (with plain loads the
+                // row loop ran one dependent load at a time: 120 us per 24 frames, 4x its instruction time)
+                const unsigned dst = (unsigned)__cvta_generic_to_shared(d + q);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(g + gx) : "memory");
+            } else {
+                uint32_t v = 0;
 #pragma unroll
                 for (int b = 0; b < 4; b++) v |= (uint32_t)__ldg(g + reflect101(gx + b, W)) << (8 * b);
+                d[q] = v;
             }
-            d[q] = v;
         }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     for (int ry = wrp; ry < RH; ry += 8) {
         uint32_t wv[NB / 4];
@@ -894,8 +901,10 @@ int run_farneback(vqa_ctx *c, const uint8_t *gray, int npairs, int h, int w, dou
     // development build only (the product build reads no environment): fused iteration and strip-height knobs
     const bool fused = getenv("VQA_FB_FUSED") && atoi(getenv("VQA_FB_FUSED"));
     const int ms_h_cap = (getenv("VQA_MS_H") && atoi(getenv("VQA_MS_H")) >= 16) ? atoi(getenv("VQA_MS_H")) : MS_H;
+    const int group = (getenv("VQA_FB_GROUP") && atoi(getenv("VQA_FB_GROUP")) >= 1) ? std::min(atoi(getenv("VQA_FB_GROUP")), npairs) : npairs;
 #else
     constexpr int ms_h_cap = MS_H;
+    const int group = npairs;
 #endif
     PolyConst pc;
     make_poly(pc);
@@ -912,7 +921,7 @@ int run_farneback(vqa_ctx *c, const uint8_t *gray, int npairs, int h, int w, dou
         GaussTaps taps;
         make_gauss(ksz, sigma, taps);
         const int mode = (lw == w && lh == h) ? 0 : ((w == 2 * lw && h == 2 * lh) ? 1 : 2);
-        dim3 gF(cdiv(lw, PY_TW), cdiv(lh, PY_TH), nf), gP(cdiv(lw, 32), cdiv(lh, 8), npairs);
+        dim3 gF(cdiv(lw, PY_TW), cdiv(lh, PY_TH), nf);
         {
             // worst-case source region of a 32x8 output tile (+ Gaussian radius), for the dynamic smem size
             const double sx = (double)w / lw, sy = (double)h / lh;
@@ -953,34 +962,45 @@ int run_farneback(vqa_ctx *c, const uint8_t *gray, int npairs, int h, int w, dou
             continue;
         }
 #endif
-        // first UpdateMatrices of the level: zero flow at the coarsest level, else the coarser flow up-sampled on the fly
-        if (k == levels) {
-            VQA_BYTES(c, 60.0 * lw * lh * npairs);
-            VQA_LAUNCH(c, k_fb_matrices<2>, gP, 256, 0, R, flow, lh, lw, M, prev, ph, pw);
-        } else {
-            VQA_BYTES(c, (60.0 * lw * lh + 8.0 * pw * ph) * npairs);
-            VQA_LAUNCH(c, k_fb_matrices<1>, gP, 256, 0, R, flow, lh, lw, M, prev, ph, pw);
-        }
-        // rows per block of the marching blur: long strips amortise the 15-row warm-up, but the small
-        // pyramid levels need shorter strips to put >= ~3 waves of blocks on 148 SMs x 8 blocks
-        int rows_pb = ms_h_cap;
-        {
-            const long want = 3L * c->sm_count * 8, per_row_strip = (long)cdiv(lw, MS_OUT) * npairs;
-            const long strips = (want + per_row_strip - 1) / per_row_strip;
-            if (strips > 0) rows_pb = (int)((lh + strips - 1) / strips);
-            if (rows_pb < 16) rows_pb = 16;
-            if (rows_pb > ms_h_cap) rows_pb = ms_h_cap;
-        }
-        const dim3 gB(cdiv(lw, MS_OUT), cdiv(lh, rows_pb), npairs);
-        for (int it = 0; it < 3; it++) {
-            const bool last = (k == 0 && it == 2);
-            VQA_BYTES(c, 28.0 * lw * lh * npairs);
-            VQA_LAUNCH(c, k_fb_blur_solve, gB, MS_W, 0, M, lh, lw, flow, rows_pb, last ? mag_sum : (double *)nullptr,
-                       (!last || flow_out) ? 1 : 0);
-            if (it < 2) {
-                VQA_BYTES(c, 68.0 * lw * lh * npairs);
-                if ((lw & 3) == 0) VQA_LAUNCH(c, k_fb_matrices_t4, dim3(cdiv(lw, 128), cdiv(lh, 8), npairs), 256, 0, R, flow, lh, lw, M);
-                else VQA_LAUNCH(c, k_fb_matrices<0>, gP, 256, 0, R, flow, lh, lw, M, prev, ph, pw);
+        const size_t lpx = (size_t)lw * lh, ppx = (size_t)pw * ph;
+        // the pairs of the chunk go through the level group by group (product build: ONE group; the development build can
+        // cut the chunk into groups whose M field stays in L2 between its writer and its reader, profiles/r02_notes.md 3)
+        for (int g0 = 0; g0 < npairs; g0 += group) {
+            const int gn = std::min(group, npairs - g0);
+            const float *Rg = R + (size_t)g0 * 5 * lpx;
+            float2 *fg = flow + (size_t)g0 * lpx;
+            const float2 *pg = prev + (size_t)g0 * ppx;
+            const dim3 gPg(cdiv(lw, 32), cdiv(lh, 8), gn);
+            // first UpdateMatrices of the level: zero flow at the coarsest level, else the coarser flow up-sampled on the fly
+            if (k == levels) {
+                VQA_BYTES(c, 60.0 * lpx * gn);
+                VQA_LAUNCH(c, k_fb_matrices<2>, gPg, 256, 0, Rg, fg, lh, lw, M, pg, ph, pw);
+            } else {
+                VQA_BYTES(c, (60.0 * lpx + 8.0 * ppx) * gn);
+                VQA_LAUNCH(c, k_fb_matrices<1>, gPg, 256, 0, Rg, fg, lh, lw, M, pg, ph, pw);
+            }
+            // rows per block of the marching blur: long strips amortise the 15-row warm-up, but the small
+            // pyramid levels need shorter strips to put >= ~3 waves of blocks on 148 SMs x 8 blocks
+            int rows_pb = ms_h_cap;
+            {
+                const long want = 3L * c->sm_count * 8, per_row_strip = (long)cdiv(lw, MS_OUT) * gn;
+                const long strips = (want + per_row_strip - 1) / per_row_strip;
+                if (strips > 0) rows_pb = (int)((lh + strips - 1) / strips);
+                if (rows_pb < 16) rows_pb = 16;
+                if (rows_pb > ms_h_cap) rows_pb = ms_h_cap;
+            }
+            const dim3 gB(cdiv(lw, MS_OUT), cdiv(lh, rows_pb), gn);
+            for (int it = 0; it < 3; it++) {
+                const bool last = (k == 0 && it == 2);
+                double *ms = last ? mag_sum + g0 : (double *)nullptr;
+                const int wf = (!last || flow_out) ? 1 : 0;
+                VQA_BYTES(c, 28.0 * lpx * gn);
+                VQA_LAUNCH(c, k_fb_blur_solve, gB, MS_W, 0, M, lh, lw, fg, rows_pb, ms, wf);
+                if (it < 2) {
+                    VQA_BYTES(c, 68.0 * lpx * gn);
+                    if ((lw & 3) == 0) VQA_LAUNCH(c, k_fb_matrices_t4, dim3(cdiv(lw, 128), cdiv(lh, 8), gn), 256, 0, Rg, fg, lh, lw, M);
+                    else VQA_LAUNCH(c, k_fb_matrices<0>, gPg, 256, 0, Rg, fg, lh, lw, M, pg, ph, pw);
+                }
             }
         }
         float2 *t = prev; prev = flow; flow = t;

@@ -30,23 +30,52 @@ __device__ __forceinline__ unsigned bilin64(int p00, int p01, int p10, int p11, 
     return (unsigned)((((b0 * (t0 >> 4)) >> 16) + ((b1 * (t1 >> 4)) >> 16) + 2) >> 2);
 }
 
+// source pixel (x, y) of a frame handed over as yuv420p planes, converted as yuv.cu converts it
+struct YuvSrc {
+    const uint8_t *y, *u, *v;
+    int sy, su, sv;
+    size_t fy, fu, fv;
+};
+__device__ __forceinline__ void yuv_bgr_at(const YuvSrc &s, int frame, int x, int y, int bgr[3])
+{
+    int cb, cg, cr;
+    yuv_chroma(s.u[frame * s.fu + (size_t)(y >> 1) * s.su + (x >> 1)], s.v[frame * s.fv + (size_t)(y >> 1) * s.sv + (x >> 1)], cb, cg, cr);
+    uint8_t B, G, R;
+    yuv_px(s.y[frame * s.fy + (size_t)y * s.sy + x], cb, cg, cr, B, G, R);
+    bgr[0] = B; bgr[1] = G; bgr[2] = R;
+}
+
+template <bool YUV>
 __global__ void __launch_bounds__(128)
-k_orb64(const uint8_t *__restrict__ bgr, size_t frame_stride, int h, int w, int *__restrict__ counts,
+k_orb64(const uint8_t *__restrict__ bgr, size_t frame_stride, YuvSrc ys, int h, int w, int *__restrict__ counts,
         int *__restrict__ dbg)
 {
     __shared__ int win[10][10];
     __shared__ int sc[4][4];
     const int frame = blockIdx.x, t = threadIdx.x;
-    const uint8_t *src = bgr + (size_t)frame * frame_stride;
     if (t < 100) {
         const int wy = t / 10, wx = t - wy * 10;
         int x0, x1, a0, a1, y0, y1, b0, b1;
         linear_tap64(27 + wx, w, false, x0, x1, a0, a1);
         linear_tap64(27 + wy, h, true, y0, y1, b0, b1);
-        const uint8_t *r0 = src + (size_t)y0 * w * 3, *r1 = src + (size_t)y1 * w * 3;
-        unsigned B = bilin64(r0[x0 * 3], r0[x1 * 3], r1[x0 * 3], r1[x1 * 3], a0, a1, b0, b1);
-        unsigned G = bilin64(r0[x0 * 3 + 1], r0[x1 * 3 + 1], r1[x0 * 3 + 1], r1[x1 * 3 + 1], a0, a1, b0, b1);
-        unsigned R = bilin64(r0[x0 * 3 + 2], r0[x1 * 3 + 2], r1[x0 * 3 + 2], r1[x1 * 3 + 2], a0, a1, b0, b1);
+        int p00[3], p01[3], p10[3], p11[3];
+        if (YUV) {
+            yuv_bgr_at(ys, frame, x0, y0, p00);
+            yuv_bgr_at(ys, frame, x1, y0, p01);
+            yuv_bgr_at(ys, frame, x0, y1, p10);
+            yuv_bgr_at(ys, frame, x1, y1, p11);
+        } else {
+            const uint8_t *src = bgr + (size_t)frame * frame_stride;
+            const uint8_t *r0 = src + (size_t)y0 * w * 3, *r1 = src + (size_t)y1 * w * 3;
+#pragma unroll
+            for (int ch = 0; ch < 3; ch++) {
+                p00[ch] = r0[x0 * 3 + ch]; p01[ch] = r0[x1 * 3 + ch];
+                p10[ch] = r1[x0 * 3 + ch]; p11[ch] = r1[x1 * 3 + ch];
+            }
+        }
+        unsigned B = bilin64(p00[0], p01[0], p10[0], p11[0], a0, a1, b0, b1);
+        unsigned G = bilin64(p00[1], p01[1], p10[1], p11[1], a0, a1, b0, b1);
+        unsigned R = bilin64(p00[2], p01[2], p10[2], p11[2], a0, a1, b0, b1);
         win[wy][wx] = (int)gray_of(B, G, R);
     }
     __syncthreads();
@@ -102,7 +131,16 @@ k_orb64(const uint8_t *__restrict__ bgr, size_t frame_stride, int h, int w, int 
 int run_orb64(vqa_ctx *c, const uint8_t *bgr, int n, int h, int w, size_t frame_stride, int *counts, int *dbg)
 {
     VQA_BYTES(c, (double)n * 100 * 12);
-    VQA_LAUNCH(c, k_orb64, n, 128, 0, bgr, frame_stride, h, w, counts, dbg);
+    VQA_LAUNCH(c, k_orb64<false>, n, 128, 0, bgr, frame_stride, YuvSrc{}, h, w, counts, dbg);
+    return VQA_OK;
+}
+
+int run_orb64_yuv(vqa_ctx *c, const uint8_t *const planes[3], const int stride[3], const size_t frame_stride[3], int n, int h,
+                  int w, int *counts)
+{
+    const YuvSrc ys{planes[0], planes[1], planes[2], stride[0], stride[1], stride[2], frame_stride[0], frame_stride[1], frame_stride[2]};
+    VQA_BYTES(c, (double)n * 100 * 12);
+    VQA_LAUNCH(c, k_orb64<true>, n, 128, 0, (const uint8_t *)nullptr, (size_t)0, ys, h, w, counts, (int *)nullptr);
     return VQA_OK;
 }
 

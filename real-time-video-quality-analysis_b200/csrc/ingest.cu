@@ -1,5 +1,5 @@
 // Ingest stage: BGR -> gray (15-bit fixed point), bit-exact INTER_LINEAR resize, the four 256-bin
-// histograms (B, G, R, gray) with warp-aggregated shared-memory atomics, and the entropies.
+// histograms (B, G, R, gray) in warp-private shared-memory copies, and the entropies.
 //
 // Replaces the cv2.cvtColor / cv2.resize / cv2.calcHist / np.log2 calls of
 // complexity_metrics.py:327-328,358-359,386,404-414,430,455-473,490-493,530-531.
@@ -10,34 +10,12 @@
 
 namespace vqa {
 
-// One lane per distinct bin does the shared-memory atomic for all lanes that hit that bin.
-template <bool AGG = true>
-__device__ __forceinline__ void hist_add(unsigned *h, unsigned bin, bool valid, int lane)
-{
-    if (!AGG) {
-        // plain shared-memory atomics, except that a warp whose lanes all hit the same bin (flat
-        // areas) issues one add: on B200 this is ~10x faster than per-bin match.any aggregation
-        // for textured frames (profiles/r01_notes.md) and keeps the flat-frame worst case at 1 atomic.
-        const unsigned vm = __ballot_sync(0xffffffffu, valid);
-        const unsigned b0 = __shfl_sync(0xffffffffu, bin, __ffs(vm | 0x80000000u) - 1);
-        if (__all_sync(0xffffffffu, !valid || bin == b0)) {
-            if (vm && lane == __ffs(vm) - 1) atomicAdd(&h[bin], (unsigned)__popc(vm));
-        } else if (valid) {
-            atomicAdd(&h[bin], 1u);
-        }
-        return;
-    }
-    unsigned key = valid ? bin : 0xffffffffu;
-    unsigned peers = __match_any_sync(0xffffffffu, key);
-    if (valid && (__ffs(peers) - 1) == lane) atomicAdd(&h[bin], (unsigned)__popc(peers));
-}
-
 constexpr int GH_THREADS = 256;
 constexpr int GH_WARPS = GH_THREADS / 32;
 
 // grid = (blocks_per_frame, n_frames).  Each thread converts groups of 16 pixels: three 128-bit
 // loads of interleaved BGR, one 128-bit store of gray.
-template <bool HIST, bool AGG>
+template <bool HIST>
 __global__ void __launch_bounds__(GH_THREADS)
 k_gray_hist(const uint8_t *__restrict__ bgr, size_t frame_stride, int P, uint8_t *__restrict__ gray,
             uint32_t *__restrict__ hist)
@@ -86,10 +64,10 @@ k_gray_hist(const uint8_t *__restrict__ bgr, size_t frame_stride, int P, uint8_t
             unsigned Y = gray_of(B, G, R);
             out[px >> 2] |= Y << ((px & 3) * 8);
             if (HIST) {
-                hist_add<AGG>(wh, B, valid, lane);
-                hist_add<AGG>(wh + 256, G, valid, lane);
-                hist_add<AGG>(wh + 512, R, valid, lane);
-                hist_add<AGG>(wh + 768, Y, valid, lane);
+                hist_add_plain(wh, B, valid, lane);
+                hist_add_plain(wh + 256, G, valid, lane);
+                hist_add_plain(wh + 512, R, valid, lane);
+                hist_add_plain(wh + 768, Y, valid, lane);
             }
         }
         if (valid) {
@@ -112,10 +90,10 @@ k_gray_hist(const uint8_t *__restrict__ bgr, size_t frame_stride, int P, uint8_t
             dst[i] = (uint8_t)Y;
         }
         if (HIST) {
-            hist_add(wh, B, valid, lane);
-            hist_add(wh + 256, G, valid, lane);
-            hist_add(wh + 512, R, valid, lane);
-            hist_add(wh + 768, Y, valid, lane);
+            hist_add_plain(wh, B, valid, lane);
+            hist_add_plain(wh + 256, G, valid, lane);
+            hist_add_plain(wh + 512, R, valid, lane);
+            hist_add_plain(wh + 768, Y, valid, lane);
         }
     }
     if (HIST) {
@@ -181,10 +159,10 @@ k_resize_bgr_gray_hist(const uint8_t *__restrict__ bgr, size_t frame_stride, int
             Y = gray_of(B, G, R);
             gray_small[(size_t)frame * total + idx] = (uint8_t)Y;
         }
-        hist_add(sh, B, valid, lane);
-        hist_add(sh + 256, G, valid, lane);
-        hist_add(sh + 512, R, valid, lane);
-        hist_add(sh + 768, Y, valid, lane);
+        hist_add_plain(sh, B, valid, lane);
+        hist_add_plain(sh + 256, G, valid, lane);
+        hist_add_plain(sh + 512, R, valid, lane);
+        hist_add_plain(sh + 768, Y, valid, lane);
     }
     __syncthreads();
     uint32_t *gh = hist + (size_t)frame * 1024;
@@ -272,7 +250,33 @@ k_sq_sum(const uint8_t *__restrict__ x, long per_frame, unsigned long long *__re
     if ((threadIdx.x & 31) == 0 && acc) atomicAdd(&out[frame], acc);
 }
 
+// sum x and sum x^2 of a gray frame from its 256-bin histogram (bins of plane 3): what k_frame_sum (DCT mean) and
+// k_sq_sum (Parseval check of the DCT energy) would re-read the frame for
+__global__ void __launch_bounds__(256)
+k_hist_moments(const uint32_t *__restrict__ hist, unsigned long long *__restrict__ sum, unsigned long long *__restrict__ sq)
+{
+    __shared__ unsigned long long r1[8], r2[8];
+    const int frame = blockIdx.x, i = threadIdx.x;
+    const unsigned long long cnt = hist[(size_t)frame * 1024 + 768 + i];
+    unsigned long long s1 = warp_sum(cnt * (unsigned long long)i), s2 = warp_sum(cnt * (unsigned long long)(i * i));
+    if ((i & 31) == 0) { r1[i >> 5] = s1; r2[i >> 5] = s2; }
+    __syncthreads();
+    if (i == 0) {
+        s1 = s2 = 0;
+        for (int k = 0; k < 8; k++) { s1 += r1[k]; s2 += r2[k]; }
+        if (sum) sum[frame] = s1;
+        if (sq) sq[frame] = s2;
+    }
+}
+
 // ------------------------------------------------------------------------------- launchers
+int run_hist_moments(vqa_ctx *c, const uint32_t *hist, int n, unsigned long long *sum, unsigned long long *sq_sum)
+{
+    if (n <= 0) return VQA_OK;
+    VQA_LAUNCH(c, k_hist_moments, n, 256, 0, hist, sum, sq_sum);
+    return VQA_OK;
+}
+
 int run_gray_hist(vqa_ctx *c, const uint8_t *bgr, int n, int h, int w, size_t frame_stride, uint8_t *gray,
                   uint32_t *hist)
 {
@@ -280,15 +284,13 @@ int run_gray_hist(vqa_ctx *c, const uint8_t *bgr, int n, int h, int w, size_t fr
     int bpf = cdiv(cdiv(P, 16), GH_THREADS * 8);
     if (bpf < 1) bpf = 1;
     dim3 grid(bpf, n);
-    static const int agg = getenv("VQA_HIST_AGG") ? atoi(getenv("VQA_HIST_AGG")) : 0;
     if (hist) {
         VQA_CUDA(c, cudaMemsetAsync(hist, 0, sizeof(uint32_t) * 1024 * (size_t)n, c->stream));
         VQA_BYTES(c, 4.0 * P * n);
-        if (agg) VQA_LAUNCH(c, (k_gray_hist<true, true>), grid, GH_THREADS, 0, bgr, frame_stride, P, gray, hist);
-        else VQA_LAUNCH(c, (k_gray_hist<true, false>), grid, GH_THREADS, 0, bgr, frame_stride, P, gray, hist);
+        VQA_LAUNCH(c, k_gray_hist<true>, grid, GH_THREADS, 0, bgr, frame_stride, P, gray, hist);
     } else {
         VQA_BYTES(c, 4.0 * P * n);
-        VQA_LAUNCH(c, (k_gray_hist<false, false>), grid, GH_THREADS, 0, bgr, frame_stride, P, gray, hist);
+        VQA_LAUNCH(c, k_gray_hist<false>, grid, GH_THREADS, 0, bgr, frame_stride, P, gray, hist);
     }
     return VQA_OK;
 }

@@ -174,6 +174,36 @@ __device__ __forceinline__ unsigned gray_of(unsigned b, unsigned g, unsigned r)
     return (3735u * b + 19235u * g + 9798u * r + (1u << 14)) >> 15;
 }
 
+// Histogram update of a warp-private shared-memory copy: plain shared-memory atomics, except that a warp whose lanes all
+// hit the same bin (flat areas) issues one add.  On B200 this is ~10x faster than per-bin match.any aggregation for
+// textured frames (profiles/r01_notes.md) and keeps the flat-frame worst case at 1 atomic.
+__device__ __forceinline__ void hist_add_plain(unsigned *h, unsigned bin, bool valid, int lane)
+{
+    const unsigned vm = __ballot_sync(0xffffffffu, valid);
+    const unsigned b0 = __shfl_sync(0xffffffffu, bin, __ffs(vm | 0x80000000u) - 1);
+    if (__all_sync(0xffffffffu, !valid || bin == b0)) {
+        if (vm && lane == __ffs(vm) - 1) atomicAdd(&h[bin], (unsigned)__popc(vm));
+    } else if (valid) {
+        atomicAdd(&h[bin], 1u);
+    }
+}
+
+// libswscale's unscaled yuv420p -> bgr24 pixel (yuv.cu): luma term y, chroma terms of the 2x2 block
+__device__ __forceinline__ void yuv_chroma(int U, int V, int &cb, int &cg, int &cr)
+{
+    const int u = (U << 3) - 1024, v = (V << 3) - 1024;
+    cb = (u * 16525) >> 16;
+    cg = ((u * -3209) >> 16) + ((v * -6660) >> 16);
+    cr = (v * 13075) >> 16;
+}
+__device__ __forceinline__ void yuv_px(int Y, int cu_b, int cg, int cv_r, uint8_t &b, uint8_t &g, uint8_t &r)
+{
+    const int y = (((Y << 3) - 128) * 9539) >> 16;
+    b = (uint8_t)min(max(y + cu_b, 0), 255);
+    g = (uint8_t)min(max(y + cg, 0), 255);
+    r = (uint8_t)min(max(y + cv_r, 0), 255);
+}
+
 // ---------------------------------------------------------------------------- stage launchers
 // ingest.cu
 int run_gray_hist(vqa_ctx *c, const uint8_t *bgr, int n, int h, int w, size_t frame_stride, uint8_t *gray,
@@ -184,12 +214,16 @@ int run_resize_u8(vqa_ctx *c, const uint8_t *src, int n, int h, int w, int cn, s
                   uint8_t *dst);
 int run_entropy(vqa_ctx *c, const uint32_t *hist, int n, float *hist_entropy, float *color_entropy);
 int run_sq_sum(vqa_ctx *c, const uint8_t *x, int n, long per_frame, unsigned long long *out);
+int run_hist_moments(vqa_ctx *c, const uint32_t *hist /* [n][4][256] */, int n, unsigned long long *sum /* [n] */,
+                     unsigned long long *sq_sum /* [n] */);
 // canny.cu
 int run_canny(vqa_ctx *c, const uint8_t *gray, int n, int h, int w, unsigned long long *counts /* [n] dev */,
               uint8_t *edges_out /* optional [n][h][w] 0/255 */);
 // fast_orb.cu
 int run_orb64(vqa_ctx *c, const uint8_t *bgr, int n, int h, int w, size_t frame_stride, int *counts /* [n] dev */,
               int *dbg = nullptr /* optional [116]: 10x10 window + 4x4 scores of frame 0 */);
+int run_orb64_yuv(vqa_ctx *c, const uint8_t *const planes[3], const int stride[3], const size_t frame_stride[3], int n, int h,
+                  int w, int *counts /* [n] dev */);
 // orb.cu: general-size ORB (pyramid, FAST, Harris, retainBest); gray rows `pitch0` bytes apart
 void orb_defaults(vqa_orb_cfg *cfg);
 int run_orb_general(vqa_ctx *c, const uint8_t *gray, int n, int h, int w, size_t frame_stride, int pitch0,
@@ -201,10 +235,11 @@ int orb_level_view(vqa_ctx *c, int level, const uint8_t **ptr, int *pitch, int *
 void orb_release(vqa_ctx *c);
 // dct.cu / dct_umma.cu
 int run_dct(vqa_ctx *c, const uint8_t *x, int n, int h, int w, int impl, float *coef /* [n][h][w] dev */,
-            double *energy /* [n] dev */);
+            double *energy /* [n] dev */, const unsigned long long *pixel_sums = nullptr /* [n] dev: sum of x per frame, if known */);
 int run_abs_diff_sum(vqa_ctx *c, const float *a, const float *b, int n, long per_frame, size_t stride_a,
                      size_t stride_b, double *out /* [n] dev */);
-int run_dct_umma(vqa_ctx *c, const uint8_t *x, int n, int h, int w, float *coef, double *energy);
+int run_dct_umma(vqa_ctx *c, const uint8_t *x, int n, int h, int w, float *coef, double *energy,
+                 const unsigned long long *pixel_sums = nullptr);
 void dct_umma_release(vqa_ctx *c);
 // farneback.cu
 int run_farneback(vqa_ctx *c, const uint8_t *gray /* [n+1][h][w] */, int npairs, int h, int w,
@@ -218,6 +253,10 @@ int run_psnr_ssim_planes(vqa_ctx *c, const uint8_t *const a[3], const uint8_t *c
 // yuv.cu
 int run_yuv420_to_bgr(vqa_ctx *c, const uint8_t *const planes[3], const int stride[3], const size_t frame_stride[3],
                       int n, int h, int w, uint8_t *bgr /* [n][h][w][3] dense */);
+bool yuv420_gray_hist_ok(const uint8_t *const planes[3], const int stride[3], const size_t frame_stride[3], int h, int w,
+                         const uint8_t *gray);
+int run_yuv420_gray_hist(vqa_ctx *c, const uint8_t *const planes[3], const int stride[3], const size_t frame_stride[3],
+                         int n, int h, int w, uint8_t *gray /* [n][h][w] */, uint32_t *hist /* [n][4][256] or nullptr */);
 // comm.cu
 void comm_release(vqa_ctx *c);
 // stats.cu

@@ -19,14 +19,6 @@
 
 namespace vqa {
 
-__device__ __forceinline__ void yuv_px(int Y, int cu_b, int cg, int cv_r, uint8_t &b, uint8_t &g, uint8_t &r)
-{
-    const int y = (((Y << 3) - 128) * 9539) >> 16;
-    b = (uint8_t)min(max(y + cu_b, 0), 255);
-    g = (uint8_t)min(max(y + cg, 0), 255);
-    r = (uint8_t)min(max(y + cv_r, 0), 255);
-}
-
 // one thread: 8 pixels x 2 rows (4 chroma samples).  grid (ceil(w/8/64), h/2, n), block 64.
 __global__ void __launch_bounds__(64)
 k_yuv420_to_bgr(const uint8_t *__restrict__ Yp, const uint8_t *__restrict__ Up, const uint8_t *__restrict__ Vp,
@@ -66,8 +58,8 @@ k_yuv420_to_bgr(const uint8_t *__restrict__ Yp, const uint8_t *__restrict__ Up, 
     uint8_t r0[24], r1[24];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-        const int u = ((int)uu[j] << 3) - 1024, v = ((int)vv[j] << 3) - 1024;
-        const int cb = (u * 16525) >> 16, cg = ((u * -3209) >> 16) + ((v * -6660) >> 16), cr = (v * 13075) >> 16;
+        int cb, cg, cr;
+        yuv_chroma(uu[j], vv[j], cb, cg, cr);
 #pragma unroll
         for (int k = 0; k < 2; k++) {
             const int p = 2 * j + k;
@@ -104,6 +96,115 @@ int run_yuv420_to_bgr(vqa_ctx *c, const uint8_t *const planes[3], const int stri
     VQA_BYTES(c, 4.5 * h * w * n);
     VQA_LAUNCH(c, k_yuv420_to_bgr, dim3(cdiv(cdiv(w, 8), 64), h / 2, n), 64, 0, planes[0], planes[1], planes[2], h, w,
                stride[0], stride[1], stride[2], frame_stride[0], frame_stride[1], frame_stride[2], bgr, vec ? 1 : 0);
+    return VQA_OK;
+}
+
+// yuv420p -> gray + the four histograms in ONE pass (native-resolution analysis of an encode handed over as planes): the
+// BGR triple of a pixel exists only in registers -- converted exactly as above, fed to OpenCV's BGR -> gray and to the
+// B / G / R / gray histograms -- so the 3 B/px BGR frame is neither written nor read back (k_yuv420_to_bgr + k_gray_hist
+// moved 8.5 B/px, this kernel 2.5).  One thread: 8 pixels x 2 rows per work item (64-bit luma loads, 32-bit chroma loads,
+// 64-bit gray stores); histograms are warp-private in shared memory like k_gray_hist's and flushed with one global atomic
+// per non-empty bin and block.  Requires the vector layout (w % 8 == 0, 8-byte aligned rows): run_yuv420_gray_hist says
+// when it does not apply.
+constexpr int YG_THREADS = 256, YG_WARPS = YG_THREADS / 32;
+
+template <bool HIST>
+__global__ void __launch_bounds__(YG_THREADS)
+k_yuv420_gray_hist(const uint8_t *__restrict__ Yp, const uint8_t *__restrict__ Up, const uint8_t *__restrict__ Vp,
+                   int h, int w, int sy, int su, int sv, size_t fy, size_t fu, size_t fv, uint8_t *__restrict__ gray,
+                   uint32_t *__restrict__ hist)
+{
+    __shared__ unsigned sh[HIST ? YG_WARPS * 1024 : 1];
+    const int frame = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned *wh = sh + (HIST ? warp * 1024 : 0);
+    if (HIST) {
+        for (int i = threadIdx.x; i < YG_WARPS * 1024; i += YG_THREADS) sh[i] = 0;
+        __syncthreads();
+    }
+    const uint8_t *yb = Yp + frame * fy, *ub = Up + frame * fu, *vb = Vp + frame * fv;
+    uint8_t *gb = gray + (size_t)frame * h * w;
+    const int wq = w >> 3, items = (h >> 1) * wq, stride = gridDim.x * YG_THREADS;
+    for (int base = blockIdx.x * YG_THREADS; base < items; base += stride) {
+        const int it = base + threadIdx.x;
+        const bool valid = it < items;
+        unsigned ya[2] = {0, 0}, yc[2] = {0, 0}, u4 = 0, v4 = 0;
+        int r2 = 0, xq = 0;
+        if (valid) {
+            r2 = it / wq;
+            xq = it - r2 * wq;
+            const uint2 a = __ldg(reinterpret_cast<const uint2 *>(yb + (size_t)(2 * r2) * sy + 8 * xq));
+            const uint2 b = __ldg(reinterpret_cast<const uint2 *>(yb + (size_t)(2 * r2 + 1) * sy + 8 * xq));
+            ya[0] = a.x; ya[1] = a.y; yc[0] = b.x; yc[1] = b.y;
+            u4 = __ldg(reinterpret_cast<const unsigned *>(ub + (size_t)r2 * su + 4 * xq));
+            v4 = __ldg(reinterpret_cast<const unsigned *>(vb + (size_t)r2 * sv + 4 * xq));
+        }
+        unsigned g0[2] = {0, 0}, g1[2] = {0, 0};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            int cb, cg, cr;
+            yuv_chroma((int)((u4 >> (8 * j)) & 255u), (int)((v4 >> (8 * j)) & 255u), cb, cg, cr);
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                const int p = 2 * j + k;
+#pragma unroll
+                for (int row = 0; row < 2; row++) {
+                    const unsigned Yv = ((row ? yc[p >> 2] : ya[p >> 2]) >> (8 * (p & 3))) & 255u;
+                    uint8_t B, G, R;
+                    yuv_px((int)Yv, cb, cg, cr, B, G, R);
+                    const unsigned gv = gray_of(B, G, R);
+                    if (row) g1[p >> 2] |= gv << (8 * (p & 3));
+                    else g0[p >> 2] |= gv << (8 * (p & 3));
+                    if (HIST) {
+                        hist_add_plain(wh, B, valid, lane);
+                        hist_add_plain(wh + 256, G, valid, lane);
+                        hist_add_plain(wh + 512, R, valid, lane);
+                        hist_add_plain(wh + 768, gv, valid, lane);
+                    }
+                }
+            }
+        }
+        if (valid) {
+            *reinterpret_cast<uint2 *>(gb + (size_t)(2 * r2) * w + 8 * xq) = make_uint2(g0[0], g0[1]);
+            *reinterpret_cast<uint2 *>(gb + (size_t)(2 * r2 + 1) * w + 8 * xq) = make_uint2(g1[0], g1[1]);
+        }
+    }
+    if (HIST) {
+        __syncthreads();
+        uint32_t *gh = hist + (size_t)frame * 1024;
+        for (int i = threadIdx.x; i < 1024; i += YG_THREADS) {
+            unsigned s = 0;
+#pragma unroll
+            for (int k = 0; k < YG_WARPS; k++) s += sh[k * 1024 + i];
+            if (s) atomicAdd(&gh[i], s);
+        }
+    }
+}
+
+bool yuv420_gray_hist_ok(const uint8_t *const planes[3], const int stride[3], const size_t frame_stride[3], int h, int w,
+                         const uint8_t *gray)
+{
+    return ((h | w) & 1) == 0 && (w % 8 == 0) && (stride[0] % 8 == 0) && (stride[1] % 4 == 0) && (stride[2] % 4 == 0) &&
+           (frame_stride[0] % 8 == 0) && (frame_stride[1] % 4 == 0) && (frame_stride[2] % 4 == 0) &&
+           (((uintptr_t)planes[0] | (uintptr_t)gray) % 8 == 0) && (((uintptr_t)planes[1] | (uintptr_t)planes[2]) % 4 == 0);
+}
+
+int run_yuv420_gray_hist(vqa_ctx *c, const uint8_t *const planes[3], const int stride[3], const size_t frame_stride[3],
+                         int n, int h, int w, uint8_t *gray, uint32_t *hist)
+{
+    if (n <= 0) return VQA_OK;
+    if (!yuv420_gray_hist_ok(planes, stride, frame_stride, h, w, gray))
+        return set_err(c, VQA_E_UNSUPPORTED, "fused yuv420p -> gray path needs the vector layout (%dx%d)", w, h);
+    int bpf = cdiv((h / 2) * (w / 8), YG_THREADS * 8);
+    if (bpf < 1) bpf = 1;
+    VQA_BYTES(c, 2.5 * h * w * n);
+    if (hist) {
+        VQA_CUDA(c, cudaMemsetAsync(hist, 0, sizeof(uint32_t) * 1024 * (size_t)n, c->stream));
+        VQA_LAUNCH(c, k_yuv420_gray_hist<true>, dim3(bpf, n), YG_THREADS, 0, planes[0], planes[1], planes[2], h, w, stride[0],
+                   stride[1], stride[2], frame_stride[0], frame_stride[1], frame_stride[2], gray, hist);
+    } else {
+        VQA_LAUNCH(c, k_yuv420_gray_hist<false>, dim3(bpf, n), YG_THREADS, 0, planes[0], planes[1], planes[2], h, w, stride[0],
+                   stride[1], stride[2], frame_stride[0], frame_stride[1], frame_stride[2], gray, hist);
+    }
     return VQA_OK;
 }
 
