@@ -599,8 +599,11 @@ __global__ void __launch_bounds__(256)
 k_fb_matrices(const float *__restrict__ R, const float2 *__restrict__ flow, int h, int w, float *__restrict__ M,
               const float2 *__restrict__ prev, int ph, int pw)
 {
-    const int pair = blockIdx.z;
-    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    // the pair is the FASTEST block index: the blocks of one image tile for consecutive pairs are scheduled together, and
+    // R of frame p+1 is both R1 of pair p and R0 of pair p+1 -- the second read hits L2 instead of DRAM (round 2; with the
+    // pair as the slowest index the two reads were one pair's 140 MB working set apart and both came from DRAM)
+    const int pair = blockIdx.x;
+    const int x = blockIdx.y * 32 + (threadIdx.x & 31), y = blockIdx.z * 8 + (threadIdx.x >> 5);
     if (x >= w || y >= h) return;
     const size_t plane = (size_t)h * w;
     const float *R0 = R + (size_t)pair * 5 * plane, *R1 = R0 + 5 * plane;
@@ -630,8 +633,8 @@ __global__ void __launch_bounds__(256)
 k_fb_matrices_t4(const float *__restrict__ R, const float2 *__restrict__ flow, int h, int w, float *__restrict__ M)
 {
     __shared__ __align__(16) float tile[8][7 * 128];               // per warp: 5 planes of R0 | interleaved flow (256)
-    const int pair = blockIdx.z, lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-    const int xw = blockIdx.x * 128, x = xw + lane * 4, y = blockIdx.y * 8 + wrp;
+    const int pair = blockIdx.x, lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;      // pair fastest: see k_fb_matrices
+    const int xw = blockIdx.y * 128, x = xw + lane * 4, y = blockIdx.z * 8 + wrp;
     if (y >= h) return;                                              // warp-uniform
     const bool have = x < w;
     const size_t plane = (size_t)h * w, o = (size_t)y * w + x;
@@ -970,7 +973,7 @@ int run_farneback(vqa_ctx *c, const uint8_t *gray, int npairs, int h, int w, dou
             const float *Rg = R + (size_t)g0 * 5 * lpx;
             float2 *fg = flow + (size_t)g0 * lpx;
             const float2 *pg = prev + (size_t)g0 * ppx;
-            const dim3 gPg(cdiv(lw, 32), cdiv(lh, 8), gn);
+            const dim3 gPg(gn, cdiv(lw, 32), cdiv(lh, 8));
             // first UpdateMatrices of the level: zero flow at the coarsest level, else the coarser flow up-sampled on the fly
             if (k == levels) {
                 VQA_BYTES(c, 60.0 * lpx * gn);
@@ -998,7 +1001,7 @@ int run_farneback(vqa_ctx *c, const uint8_t *gray, int npairs, int h, int w, dou
                 VQA_LAUNCH(c, k_fb_blur_solve, gB, MS_W, 0, M, lh, lw, fg, rows_pb, ms, wf);
                 if (it < 2) {
                     VQA_BYTES(c, 68.0 * lpx * gn);
-                    if ((lw & 3) == 0) VQA_LAUNCH(c, k_fb_matrices_t4, dim3(cdiv(lw, 128), cdiv(lh, 8), gn), 256, 0, Rg, fg, lh, lw, M);
+                    if ((lw & 3) == 0) VQA_LAUNCH(c, k_fb_matrices_t4, dim3(gn, cdiv(lw, 128), cdiv(lh, 8)), 256, 0, Rg, fg, lh, lw, M);
                     else VQA_LAUNCH(c, k_fb_matrices<0>, gPg, 256, 0, Rg, fg, lh, lw, M, pg, ph, pw);
                 }
             }

@@ -55,6 +55,7 @@ k_gray_hist(const uint8_t *__restrict__ bgr, size_t frame_stride, int P, uint8_t
             for (int i = 0; i < 12; i++) w[i] = 0;
         }
         unsigned out[4] = {0, 0, 0, 0};
+        const unsigned vm = __ballot_sync(0xffffffffu, valid);
 #pragma unroll
         for (int px = 0; px < 16; px++) {
             const int o = px * 3;
@@ -63,12 +64,7 @@ k_gray_hist(const uint8_t *__restrict__ bgr, size_t frame_stride, int P, uint8_t
             unsigned R = (w[(o + 2) >> 2] >> (((o + 2) & 3) * 8)) & 255u;
             unsigned Y = gray_of(B, G, R);
             out[px >> 2] |= Y << ((px & 3) * 8);
-            if (HIST) {
-                hist_add_plain(wh, B, valid, lane);
-                hist_add_plain(wh + 256, G, valid, lane);
-                hist_add_plain(wh + 512, R, valid, lane);
-                hist_add_plain(wh + 768, Y, valid, lane);
-            }
+            if (HIST) hist_add4(wh, B, G, R, Y, valid, vm, lane);
         }
         if (valid) {
             if (vec) {

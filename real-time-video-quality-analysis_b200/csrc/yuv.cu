@@ -139,6 +139,7 @@ k_yuv420_gray_hist(const uint8_t *__restrict__ Yp, const uint8_t *__restrict__ U
             v4 = __ldg(reinterpret_cast<const unsigned *>(vb + (size_t)r2 * sv + 4 * xq));
         }
         unsigned g0[2] = {0, 0}, g1[2] = {0, 0};
+        const unsigned vm = __ballot_sync(0xffffffffu, valid);
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             int cb, cg, cr;
@@ -154,12 +155,7 @@ k_yuv420_gray_hist(const uint8_t *__restrict__ Yp, const uint8_t *__restrict__ U
                     const unsigned gv = gray_of(B, G, R);
                     if (row) g1[p >> 2] |= gv << (8 * (p & 3));
                     else g0[p >> 2] |= gv << (8 * (p & 3));
-                    if (HIST) {
-                        hist_add_plain(wh, B, valid, lane);
-                        hist_add_plain(wh + 256, G, valid, lane);
-                        hist_add_plain(wh + 512, R, valid, lane);
-                        hist_add_plain(wh + 768, gv, valid, lane);
-                    }
+                    if (HIST) hist_add4(wh, B, G, R, gv, valid, vm, lane);
                 }
             }
         }

@@ -427,6 +427,18 @@ def test_streaming_clip_equals_whole_clip(vqa, ctx, small_clip, tmp_path):
         np.testing.assert_allclose(rows["temporal_dct"][1:], whole["temporal_dct"][1:], rtol=1e-6)
         got = cm.calculate_average_scene_complexity(path, 64, 64, frame_interval=interval)
         assert all(isinstance(v, np.float64) and np.isfinite(v) for v in got)
+        # ... and against the CPU restatement of the reference on the same decoded frames (not only device vs device):
+        # the reference's call structure on cv2 itself when importable (oracle/ref_port.py)
+        cap, dec = cv2.VideoCapture(path), []
+        while True:
+            ok, f = cap.read()
+            if not ok:
+                break
+            dec.append(f)
+        cap.release()
+        want = RP.average_scene_complexity(np.stack(dec), 64, 64, frame_interval=interval, engine="cv2")
+        assert float(got[3]) == pytest.approx(float(want[3]), rel=1e-12) and float(got[4]) == pytest.approx(float(want[4]), rel=1e-12)
+        np.testing.assert_allclose([float(v) for v in got[:7]], [float(v) for v in want[:7]], rtol=RTOL)
     assert all(np.isnan(v) for v in cm.calculate_average_scene_complexity(str(tmp_path / "missing.mp4"), 64, 64)[:6])
 
 

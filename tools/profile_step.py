@@ -27,3 +27,10 @@ rows, fr = step()
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()
 print("ok", rows["motion"][1:4], fr["psnr_avg"][:2])
+if os.environ.get("VQA_PROF_REPORT"):                      # the library's own per-kernel table of the SAME step (declared bytes)
+    import json
+    ctx.kernel_profile(True)
+    step()
+    rep = ctx.kernel_report()
+    ctx.kernel_profile(False)
+    json.dump({"frames": F, "height": H, "width": W, "kernels": rep}, open(os.environ["VQA_PROF_REPORT"], "w"), indent=1)
