@@ -144,7 +144,11 @@ int vqa_init(int device, vqa_ctx **out)
         cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->fb_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_fb_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_fb_stagger, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_fb_join, cudaEventDisableTiming) != cudaSuccess) {
         delete c;
         return set_err(nullptr, VQA_E_CUDA, "stream creation failed");
     }
@@ -174,6 +178,7 @@ void vqa_destroy(vqa_ctx *c)
     cudaStreamSynchronize(c->stream);
     cudaStreamSynchronize(c->copy_stream);
     cudaStreamSynchronize(c->side_stream);
+    cudaStreamSynchronize(c->fb_stream);
     comm_release(c);
     dct_umma_release(c);
     orb_release(c);
@@ -186,6 +191,10 @@ void vqa_destroy(vqa_ctx *c)
     if (c->own_stream) cudaStreamDestroy(c->stream);
     cudaStreamDestroy(c->copy_stream);
     cudaStreamDestroy(c->side_stream);
+    cudaStreamDestroy(c->fb_stream);
+    cudaEventDestroy(c->ev_fb_fork);
+    cudaEventDestroy(c->ev_fb_stagger);
+    cudaEventDestroy(c->ev_fb_join);
     cudaEventDestroy(c->ev_fork);
     cudaEventDestroy(c->ev_join);
     delete c;
@@ -350,6 +359,7 @@ int complexity_impl(vqa_ctx *c, const uint8_t *bgr, int n, int h, int w, size_t 
     const int rc = complexity_body(c, bgr, n, h, w, frame_stride, halo, on_device, cfg, out, side, yuv);
     if (rc != VQA_OK && c) {
         if (c->side_stream) cudaStreamSynchronize(c->side_stream);
+        if (c->fb_stream) cudaStreamSynchronize(c->fb_stream);
         if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
         if (c->stream) cudaStreamSynchronize(c->stream);
         cudaGetLastError();                                  // the error is already recorded in c->err

@@ -881,6 +881,8 @@ static void make_poly(PolyConst &pc)
 #include "farneback_fused.cuh"
 #endif
 
+constexpr bool FB_DUAL_STREAMS = false;            // two-stream staggered schedule of a level (see run_farneback)
+
 int run_farneback(vqa_ctx *c, const uint8_t *gray, int npairs, int h, int w, double *mag_sum, float *flow_out)
 {
     if (npairs <= 0) return VQA_OK;
@@ -905,7 +907,9 @@ int run_farneback(vqa_ctx *c, const uint8_t *gray, int npairs, int h, int w, dou
     const bool fused = getenv("VQA_FB_FUSED") && atoi(getenv("VQA_FB_FUSED"));
     const int ms_h_cap = (getenv("VQA_MS_H") && atoi(getenv("VQA_MS_H")) >= 16) ? atoi(getenv("VQA_MS_H")) : MS_H;
     const int group = (getenv("VQA_FB_GROUP") && atoi(getenv("VQA_FB_GROUP")) >= 1) ? std::min(atoi(getenv("VQA_FB_GROUP")), npairs) : npairs;
+    const bool dual = getenv("VQA_FB_DUAL") ? atoi(getenv("VQA_FB_DUAL")) != 0 : FB_DUAL_STREAMS;
 #else
+    constexpr bool dual = FB_DUAL_STREAMS;
     constexpr int ms_h_cap = MS_H;
     const int group = npairs;
 #endif
@@ -965,11 +969,10 @@ int run_farneback(vqa_ctx *c, const uint8_t *gray, int npairs, int h, int w, dou
             continue;
         }
 #endif
+        // One group of pairs through the three iterations of the level, on the context's current stream.  `after_first`
+        // is recorded behind the group's first kernel (the stagger of the two-stream schedule below).
         const size_t lpx = (size_t)lw * lh, ppx = (size_t)pw * ph;
-        // the pairs of the chunk go through the level group by group (product build: ONE group; the development build can
-        // cut the chunk into groups whose M field stays in L2 between its writer and its reader, profiles/r02_notes.md 3)
-        for (int g0 = 0; g0 < npairs; g0 += group) {
-            const int gn = std::min(group, npairs - g0);
+        auto run_group = [&](int g0, int gn, float *Mg, cudaEvent_t after_first) -> int {
             const float *Rg = R + (size_t)g0 * 5 * lpx;
             float2 *fg = flow + (size_t)g0 * lpx;
             const float2 *pg = prev + (size_t)g0 * ppx;
@@ -977,11 +980,12 @@ int run_farneback(vqa_ctx *c, const uint8_t *gray, int npairs, int h, int w, dou
             // first UpdateMatrices of the level: zero flow at the coarsest level, else the coarser flow up-sampled on the fly
             if (k == levels) {
                 VQA_BYTES(c, 60.0 * lpx * gn);
-                VQA_LAUNCH(c, k_fb_matrices<2>, gPg, 256, 0, Rg, fg, lh, lw, M, pg, ph, pw);
+                VQA_LAUNCH(c, k_fb_matrices<2>, gPg, 256, 0, Rg, fg, lh, lw, Mg, pg, ph, pw);
             } else {
                 VQA_BYTES(c, (60.0 * lpx + 8.0 * ppx) * gn);
-                VQA_LAUNCH(c, k_fb_matrices<1>, gPg, 256, 0, Rg, fg, lh, lw, M, pg, ph, pw);
+                VQA_LAUNCH(c, k_fb_matrices<1>, gPg, 256, 0, Rg, fg, lh, lw, Mg, pg, ph, pw);
             }
+            if (after_first) VQA_CUDA(c, cudaEventRecord(after_first, c->stream));
             // rows per block of the marching blur: long strips amortise the 15-row warm-up, but the small
             // pyramid levels need shorter strips to put >= ~3 waves of blocks on 148 SMs x 8 blocks
             int rows_pb = ms_h_cap;
@@ -998,13 +1002,40 @@ int run_farneback(vqa_ctx *c, const uint8_t *gray, int npairs, int h, int w, dou
                 double *ms = last ? mag_sum + g0 : (double *)nullptr;
                 const int wf = (!last || flow_out) ? 1 : 0;
                 VQA_BYTES(c, 28.0 * lpx * gn);
-                VQA_LAUNCH(c, k_fb_blur_solve, gB, MS_W, 0, M, lh, lw, fg, rows_pb, ms, wf);
+                VQA_LAUNCH(c, k_fb_blur_solve, gB, MS_W, 0, Mg, lh, lw, fg, rows_pb, ms, wf);
                 if (it < 2) {
                     VQA_BYTES(c, 68.0 * lpx * gn);
-                    if ((lw & 3) == 0) VQA_LAUNCH(c, k_fb_matrices_t4, dim3(gn, cdiv(lw, 128), cdiv(lh, 8)), 256, 0, Rg, fg, lh, lw, M);
-                    else VQA_LAUNCH(c, k_fb_matrices<0>, gPg, 256, 0, Rg, fg, lh, lw, M, pg, ph, pw);
+                    if ((lw & 3) == 0) VQA_LAUNCH(c, k_fb_matrices_t4, dim3(gn, cdiv(lw, 128), cdiv(lh, 8)), 256, 0, Rg, fg, lh, lw, Mg);
+                    else VQA_LAUNCH(c, k_fb_matrices<0>, gPg, 256, 0, Rg, fg, lh, lw, Mg, pg, ph, pw);
                 }
             }
+            return VQA_OK;
+        };
+        if (dual && npairs >= 8 && !c->ktiming) {
+            // Two-stream schedule: the chain alternates a DRAM-bound kernel (UpdateMatrices, 0.75-0.84 of the copy peak, issue
+            // slots half idle) with an issue-bound one (the marching blur, DRAM half idle).  The pairs are cut in two halves on
+            // two streams, the second ONE KERNEL BEHIND the first, so that a blur of one half always runs next to an
+            // UpdateMatrices of the other and the two share the SMs instead of taking turns.
+            const int ga = (npairs + 1) / 2, gb = npairs - ga;
+            cudaStream_t main_stream = c->stream;
+            VQA_CUDA(c, cudaEventRecord(c->ev_fb_fork, main_stream));
+            VQA_CUDA(c, cudaStreamWaitEvent(c->fb_stream, c->ev_fb_fork, 0));
+            if (int rc = run_group(0, ga, M, c->ev_fb_stagger)) return rc;
+            {
+                c->stream = c->fb_stream;
+                cudaError_t e = cudaStreamWaitEvent(c->fb_stream, c->ev_fb_stagger, 0);
+                int rc = e == cudaSuccess ? run_group(ga, gb, M + (size_t)ga * m_pair, nullptr) : VQA_E_CUDA;
+                if (rc == VQA_OK && cudaEventRecord(c->ev_fb_join, c->fb_stream) != cudaSuccess) rc = VQA_E_CUDA;
+                c->stream = main_stream;
+                if (rc) return rc == VQA_E_CUDA ? set_err(c, VQA_E_CUDA, "two-stream Farneback schedule: %s", cudaGetErrorString(cudaGetLastError())) : rc;
+            }
+            VQA_CUDA(c, cudaStreamWaitEvent(main_stream, c->ev_fb_join, 0));
+        } else {
+            // the pairs of the chunk go through the level group by group (product build: ONE group; the development build can
+            // cut the chunk into groups whose M field stays in L2 between its writer and its reader: measured negative,
+            // profiles/r02_notes.md 3)
+            for (int g0 = 0; g0 < npairs; g0 += group)
+                if (int rc = run_group(g0, std::min(group, npairs - g0), M, nullptr)) return rc;
         }
         float2 *t = prev; prev = flow; flow = t;
         ph = lh; pw = lw;

@@ -40,6 +40,8 @@ struct vqa_ctx {
     cudaStream_t copy_stream = nullptr;
     cudaStream_t side_stream = nullptr;          // Canny / ORB / DCT chain of a chunk, concurrent with the Farneback chain
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t fb_stream = nullptr;            // second half of the pairs of a Farneback level, one kernel behind the first half
+    cudaEvent_t ev_fb_fork = nullptr, ev_fb_stagger = nullptr, ev_fb_join = nullptr;
     bool own_stream = false;
     int sm_count = 148;
     char err[512] = {0};
