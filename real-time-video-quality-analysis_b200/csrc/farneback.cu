@@ -11,7 +11,10 @@
 //   (last blur pass)    sum sqrt(fx^2 + fy^2) at level 0, fused into k_fb_blur_solve
 //
 // R is computed once per frame and serves the frame both as "next" of one pair and as "prev"
-// of the following pair.  R, M and flow stay fp32 (reduced precision does not survive flat
+// of the following pair.  R and M are stored per pixel as one float4 (components 0..3) + one float (component 4) in
+// two arrays: the four bilinear taps of UpdateMatrices are 4 x (128-bit + 32-bit) loads instead of 20 scalar gathers,
+// the marching blur reads a row as 2 loads instead of 5 (round 2; planar storage made both kernels L1-bound).
+// R, M and flow stay fp32 (reduced precision does not survive flat
 // content).  Roofline: HBM.
 #include <math.h>
 #include <stdlib.h>
@@ -381,7 +384,7 @@ __device__ __forceinline__ void pe_load_tile(float (*tile)[PE_P], const float *_
 }
 
 __global__ void __launch_bounds__(256)
-k_fb_polyexp(const float *__restrict__ I, int h, int w, PolyConst pc, float *__restrict__ R)
+k_fb_polyexp(const float *__restrict__ I, int h, int w, PolyConst pc, float4 *__restrict__ R4, float *__restrict__ Rs)
 {
     extern __shared__ __align__(16) float pe_smem[];             // PE_SMEM bytes (> 48 KB: opt-in dynamic)
     float (*tile)[PE_TH + 2 * PE_R][PE_P] = reinterpret_cast<float (*)[PE_TH + 2 * PE_R][PE_P]>(pe_smem);
@@ -464,15 +467,17 @@ k_fb_polyexp(const float *__restrict__ I, int h, int w, PolyConst pc, float *__r
                     o[3][j] = (float)(b1 * (float)pc.ig03 + b4 * (float)pc.ig33);
                     o[4][j] = (float)(b6 * (float)pc.ig55);
                 }
-                float *dst = R + (size_t)frame * 5 * plane + (size_t)gy * w + gx0;
-                const bool vec = (w & 3) == 0 && gx0 + 4 <= w;          // planes are 256-byte aligned, w % 4 == 0 keeps rows aligned
+                const size_t o0 = (size_t)frame * plane + (size_t)gy * w + gx0;
+                float4 *d4 = R4 + o0;
+                float *d1 = Rs + o0;
+                const bool vec = (w & 3) == 0 && gx0 + 4 <= w;          // arrays are 256-byte aligned, w % 4 == 0 keeps rows aligned
 #pragma unroll
-                for (int ch = 0; ch < 5; ch++) {
-                    if (vec) *reinterpret_cast<float4 *>(dst + ch * plane) = make_float4(o[ch][0], o[ch][1], o[ch][2], o[ch][3]);
-                    else
-                        for (int j = 0; j < 4; j++)
-                            if (gx0 + j < w) dst[ch * plane + j] = o[ch][j];
-                }
+                for (int j = 0; j < 4; j++)
+                    if (vec || gx0 + j < w) d4[j] = make_float4(o[0][j], o[1][j], o[2][j], o[3][j]);
+                if (vec) *reinterpret_cast<float4 *>(d1) = make_float4(o[4][0], o[4][1], o[4][2], o[4][3]);
+                else
+                    for (int j = 0; j < 4; j++)
+                        if (gx0 + j < w) d1[j] = o[4][j];
             }
         }
         __syncthreads();                                     // v0..v2 and this tile buffer are rewritten next round
@@ -519,21 +524,10 @@ __device__ __forceinline__ float2 fb_upsampled_flow(const float2 *__restrict__ p
     return o;
 }
 
-// FarnebackUpdateMatrices for one pixel: returns the 5 entries of M
-__device__ __forceinline__ void fb_matrix_core(float q0, float q1, float q2, float q3, float q4,
-                                               const float *__restrict__ R1, size_t plane, int x, int y, int h, int w,
-                                               float2 f, float m[5]);
-
-__device__ __forceinline__ void fb_matrix_at(const float *__restrict__ R0, const float *__restrict__ R1, size_t plane,
-                                             int x, int y, int h, int w, float2 f, float m[5])
-{
-    const size_t o = (size_t)y * w + x;
-    fb_matrix_core(R0[o], R0[plane + o], R0[2 * plane + o], R0[3 * plane + o], R0[4 * plane + o], R1, plane, x, y, h, w, f, m);
-}
-
-__device__ __forceinline__ void fb_matrix_core(float q0, float q1, float q2, float q3, float q4,
-                                               const float *__restrict__ R1, size_t plane, int x, int y, int h, int w,
-                                               float2 f, float m[5])
+// FarnebackUpdateMatrices for one pixel: returns the 5 entries of M.  q = R of the previous frame at the pixel,
+// R1_4 / R1s = R of the next frame (float4 + float arrays), f = the flow at the pixel.
+__device__ __forceinline__ void fb_matrix_core(float4 q, float q4, const float4 *__restrict__ R1_4, const float *__restrict__ R1s,
+                                               int x, int y, int h, int w, float2 f, float m[5])
 {
     const float dx = f.x, dy = f.y;
     float fx = (float)x + dx, fy = (float)y + dy;
@@ -543,25 +537,27 @@ __device__ __forceinline__ void fb_matrix_core(float q0, float q1, float q2, flo
     float r2, r3, r4, r5, r6;
     if ((unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1)) {
         const float a00 = (1.f - fx) * (1.f - fy), a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy;
-        const size_t p = (size_t)y1 * w + x1;
-#define FB_TAP(c) (a00 * R1[(c) * plane + p] + a01 * R1[(c) * plane + p + 1] + a10 * R1[(c) * plane + p + w] + a11 * R1[(c) * plane + p + w + 1])
-        r2 = FB_TAP(0);
-        r3 = FB_TAP(1);
-        r4 = FB_TAP(2);
-        r5 = FB_TAP(3);
-        r6 = FB_TAP(4);
+        const int p = y1 * w + x1;
+        const float4 t00 = __ldg(R1_4 + p), t01 = __ldg(R1_4 + p + 1), t10 = __ldg(R1_4 + p + w), t11 = __ldg(R1_4 + p + w + 1);
+        const float s00 = __ldg(R1s + p), s01 = __ldg(R1s + p + 1), s10 = __ldg(R1s + p + w), s11 = __ldg(R1s + p + w + 1);
+#define FB_TAP(v00, v01, v10, v11) (a00 * (v00) + a01 * (v01) + a10 * (v10) + a11 * (v11))
+        r2 = FB_TAP(t00.x, t01.x, t10.x, t11.x);
+        r3 = FB_TAP(t00.y, t01.y, t10.y, t11.y);
+        r4 = FB_TAP(t00.z, t01.z, t10.z, t11.z);
+        r5 = FB_TAP(t00.w, t01.w, t10.w, t11.w);
+        r6 = FB_TAP(s00, s01, s10, s11);
 #undef FB_TAP
-        r4 = (q2 + r4) * 0.5f;
-        r5 = (q3 + r5) * 0.5f;
+        r4 = (q.z + r4) * 0.5f;
+        r5 = (q.w + r5) * 0.5f;
         r6 = (q4 + r6) * 0.25f;
     } else {
         r2 = r3 = 0.f;
-        r4 = q2;
-        r5 = q3;
+        r4 = q.z;
+        r5 = q.w;
         r6 = q4 * 0.5f;
     }
-    r2 = (q0 - r2) * 0.5f;
-    r3 = (q1 - r3) * 0.5f;
+    r2 = (q.x - r2) * 0.5f;
+    r3 = (q.y - r3) * 0.5f;
     r2 += r4 * dy + r6 * dx;
     r3 += r6 * dy + r5 * dx;
     if ((unsigned)(x - 5) >= (unsigned)(w - 10) || (unsigned)(y - 5) >= (unsigned)(h - 10)) {
@@ -579,99 +575,33 @@ __device__ __forceinline__ void fb_matrix_core(float q0, float q1, float q2, flo
     m[4] = r6 * r2 + r5 * r3;
 }
 
-// Layout of the M field (5 floats per pixel): the linear pixel index p = y*w + x is cut into
-// super-chunks of FB_MS pixels and each super-chunk stores its five planes back to back:
-// [pair][p / FB_MS][plane][p % FB_MS].  Access patterns are those of plain planar storage (each plane a
-// contiguous stream; a layout with the planes of 32 pixels adjacent measured 20 % slower in the
-// UpdateMatrices writer), but the five planes of a pixel sit at the COMPILE-TIME offsets c * 256 KB
-// from one address, so the marching blur kernel issues its ten loads per row from two pointers
-// (runtime plane strides cost a 64-bit add per load and made that kernel issue-bound).
-constexpr int FB_MS_LOG = 16, FB_MS = 1 << FB_MS_LOG;
-__host__ __device__ __forceinline__ size_t fb_m_pair_floats(int h, int w)
-{
-    return (((size_t)h * w + FB_MS - 1) >> FB_MS_LOG) * 5 * FB_MS;
-}
-__device__ __forceinline__ unsigned fb_m_index(unsigned p) { return p + ((p >> FB_MS_LOG) << (FB_MS_LOG + 2)); }
-
-// INIT 0: flow read from memory; 1: flow up-sampled from the previous (coarser) level; 2: zero flow
+// UpdateMatrices, one pixel per lane (32 x 8 pixels per block).  INIT 0: flow read from memory; 1: flow up-sampled on
+// the fly from the previous (coarser) level (first UpdateMatrices of a level; never stored); 2: zero flow (coarsest).
+// Per pixel: R0 = 128-bit + 32-bit load, flow = 64-bit load, the four taps of R1 = 4 x (128-bit + 32-bit) loads, M =
+// 128-bit + 32-bit store, every one coalesced over the 32 adjacent pixels of a warp.  (Round 1 kept R and M planar: 5 + 20
+// scalar loads per pixel, a transposed 4-pixel variant to make them 128-bit, and both at 79-89 % of the L1 data pipe.)
+// The pair is the FASTEST block index: the blocks of one image tile for consecutive pairs are scheduled together, and R
+// of frame p+1 is both R1 of pair p and R0 of pair p+1 -- the second read hits L2 instead of DRAM (with the pair as the
+// slowest index the two reads were one pair's 140 MB working set apart: -22 % DRAM bytes, profiles/r02_notes.md 5).
 template <int INIT>
 __global__ void __launch_bounds__(256)
-k_fb_matrices(const float *__restrict__ R, const float2 *__restrict__ flow, int h, int w, float *__restrict__ M,
-              const float2 *__restrict__ prev, int ph, int pw)
+k_fb_matrices(const float4 *__restrict__ R4, const float *__restrict__ Rs, const float2 *__restrict__ flow, int h, int w,
+              float4 *__restrict__ M4, float *__restrict__ Ms, const float2 *__restrict__ prev, int ph, int pw)
 {
-    // the pair is the FASTEST block index: the blocks of one image tile for consecutive pairs are scheduled together, and
-    // R of frame p+1 is both R1 of pair p and R0 of pair p+1 -- the second read hits L2 instead of DRAM (round 2; with the
-    // pair as the slowest index the two reads were one pair's 140 MB working set apart and both came from DRAM)
     const int pair = blockIdx.x;
     const int x = blockIdx.y * 32 + (threadIdx.x & 31), y = blockIdx.z * 8 + (threadIdx.x >> 5);
     if (x >= w || y >= h) return;
-    const size_t plane = (size_t)h * w;
-    const float *R0 = R + (size_t)pair * 5 * plane, *R1 = R0 + 5 * plane;
+    const size_t plane = (size_t)h * w, o = (size_t)pair * plane + (size_t)y * w + x;
+    const float4 q = __ldg(R4 + o);
+    const float q4 = __ldg(Rs + o);
     float2 f;
-    if (INIT == 0) f = flow[(size_t)pair * plane + (size_t)y * w + x];
+    if (INIT == 0) f = __ldg(flow + o);
     else if (INIT == 1) f = fb_upsampled_flow(prev + (size_t)pair * ph * pw, ph, pw, x, y, h, w);
     else f = make_float2(0.f, 0.f);
     float m[5];
-    fb_matrix_at(R0, R1, plane, x, y, h, w, f, m);
-    float *dst = M + (size_t)pair * fb_m_pair_floats(h, w) + fb_m_index((unsigned)(y * w + x));
-#pragma unroll
-    for (int c = 0; c < 5; c++) dst[c * FB_MS] = m[c];
-}
-
-// UpdateMatrices with the flow read from memory, "transposed gather".  A plain 4-pixels-per-lane kernel
-// (round 1's k_fb_matrices_v4, removed) issues the 20 scalar R1 gathers per pixel with the lanes of a warp
-// 16 bytes apart, so every gather instruction touches 16-20 sectors of which 4 bytes each are used -- 637 M
-// sectors per level-0 launch against 237 M for the one-pixel-per-lane kernel, L1 data pipe 88 % busy.  Here
-// R0, flow and M move as 128-bit accesses (4 pixels per lane), but the per-pixel work runs with the lanes of
-// a warp on 32 ADJACENT pixels (4 rounds per 128-pixel row segment): the operands are transposed through
-// a per-warp shared-memory tile (conflict-free both ways), the gathers of a warp then fall into 1-2
-// cache lines, and the results go back through the same tile.  Arithmetic per pixel is fb_matrix_core,
-// unchanged, so M is bit-identical to k_fb_matrices<0>'s.  Requires w % 4 == 0.  Flow read from memory (the first
-// UpdateMatrices of a level up-samples the coarser flow in k_fb_matrices<1>: a transposed variant of that
-// measured 25 % slower at 63 registers).
-__global__ void __launch_bounds__(256)
-k_fb_matrices_t4(const float *__restrict__ R, const float2 *__restrict__ flow, int h, int w, float *__restrict__ M)
-{
-    __shared__ __align__(16) float tile[8][7 * 128];               // per warp: 5 planes of R0 | interleaved flow (256)
-    const int pair = blockIdx.x, lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;      // pair fastest: see k_fb_matrices
-    const int xw = blockIdx.y * 128, x = xw + lane * 4, y = blockIdx.z * 8 + wrp;
-    if (y >= h) return;                                              // warp-uniform
-    const bool have = x < w;
-    const size_t plane = (size_t)h * w, o = (size_t)y * w + x;
-    const float *R0 = R + (size_t)pair * 5 * plane, *R1 = R0 + 5 * plane;
-    float *t = tile[wrp];
-    if (have) {
-#pragma unroll
-        for (int c = 0; c < 5; c++)
-            *reinterpret_cast<float4 *>(t + c * 128 + lane * 4) = __ldg(reinterpret_cast<const float4 *>(R0 + c * plane + o));
-        *reinterpret_cast<float4 *>(t + 640 + lane * 8) = __ldg(reinterpret_cast<const float4 *>(flow + (size_t)pair * plane + o));
-        *reinterpret_cast<float4 *>(t + 640 + lane * 8 + 4) = __ldg(reinterpret_cast<const float4 *>(flow + (size_t)pair * plane + o + 2));
-    }
-    __syncwarp();
-    float m[4][5];
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        const int g = 32 * j + lane;                                 // pixel of this lane in round j
-        if (xw + g < w) {
-            const float2 f = *reinterpret_cast<const float2 *>(t + 640 + 2 * g);
-            fb_matrix_core(t[g], t[128 + g], t[256 + g], t[384 + g], t[512 + g], R1, plane, xw + g, y, h, w, f, m[j]);
-        } else {
-#pragma unroll
-            for (int c = 0; c < 5; c++) m[j][c] = 0.f;
-        }
-    }
-    __syncwarp();
-#pragma unroll
-    for (int j = 0; j < 4; j++)
-#pragma unroll
-        for (int c = 0; c < 5; c++) t[c * 128 + 32 * j + lane] = m[j][c];
-    __syncwarp();
-    if (have) {
-        float *dst = M + (size_t)pair * fb_m_pair_floats(h, w) + fb_m_index((unsigned)(y * w + x));
-#pragma unroll
-        for (int c = 0; c < 5; c++)
-            *reinterpret_cast<float4 *>(dst + c * FB_MS) = *reinterpret_cast<const float4 *>(t + c * 128 + lane * 4);
-    }
+    fb_matrix_core(q, q4, R4 + (size_t)(pair + 1) * plane, Rs + (size_t)(pair + 1) * plane, x, y, h, w, f, m);
+    M4[o] = make_float4(m[0], m[1], m[2], m[3]);
+    Ms[o] = m[4];
 }
 
 constexpr int MS_W = 128, MS_OUT = 112, MS_R = 7, MS_H = 96, MS_SEG = 8;
@@ -700,21 +630,23 @@ constexpr int MS_VP = 144;
 //   * the horizontal 15-tap sums are plain float sums (core + suffix + prefix, no sliding window, so
 //     no error persists) with a dependent chain of 8;
 //   * the 2x2 solve runs in float with FMA-recovered product errors (no conversions);
-//   * M in a layout whose plane offsets are compile-time constants (ten loads from two pointers);
+//   * M stored per pixel as float4 + float: a row entering / leaving the window is 2 loads instead of 5 (round 1 kept M
+//     planar in 64 Ki-pixel super-chunks so that the ten loads came from two pointers);
 //   * the vertical 15-row running sums are DOUBLE registers: 10 DADD + 15 conversions per row.  A plain
 //     float running sum would keep eps*|edge value| of error in flat areas below strong edges (OpenCV
 //     uses double here too); float-float pairs updated with TwoSum measured 8 % slower, evaluating the
 //     next UpdateMatrices in the epilogue 7 % slower (profiles/r01_notes.md; both variants removed).
 // The new flow is stored; on the last iteration of level 0 the caller may ask for sum |flow| instead.
 __global__ void __launch_bounds__(MS_W)
-k_fb_blur_solve(const float *__restrict__ M, int h, int w, float2 *__restrict__ flow, int rows_per_block,
-                double *__restrict__ mag_sum, int write_flow)
+k_fb_blur_solve(const float4 *__restrict__ M4, const float *__restrict__ Ms, int h, int w, float2 *__restrict__ flow,
+                int rows_per_block, double *__restrict__ mag_sum, int write_flow)
 {
     __shared__ __align__(16) float row[5][MS_VP];
     __shared__ __align__(16) float hs[5][MS_VP];
     const int pair = blockIdx.z, t = threadIdx.x;
     const size_t plane = (size_t)h * w;
-    const float *src = M + (size_t)pair * fb_m_pair_floats(h, w);
+    const float4 *src4 = M4 + (size_t)pair * plane;
+    const float *src1 = Ms + (size_t)pair * plane;
     const int sx0 = blockIdx.x * MS_OUT, y0 = blockIdx.y * rows_per_block;
     const int gx = clampi(sx0 - 8 + t, 0, w - 1);
     const int y_end = min(y0 + rows_per_block, h);
@@ -722,11 +654,10 @@ k_fb_blur_solve(const float *__restrict__ M, int h, int w, float2 *__restrict__ 
 #pragma unroll
     for (int c = 0; c < 5; c++) vd[c] = 0.0;
     for (int k = -MS_R; k <= MS_R; k++) {
-        const float *p = src + fb_m_index((unsigned)(clampi(y0 + k, 0, h - 1) * w + gx));
-#pragma unroll
-        for (int c = 0; c < 5; c++) {
-            vd[c] += (double)__ldg(p + c * FB_MS);
-        }
+        const int p = clampi(y0 + k, 0, h - 1) * w + gx;
+        const float4 v = __ldg(src4 + p);
+        vd[0] += (double)v.x; vd[1] += (double)v.y; vd[2] += (double)v.z; vd[3] += (double)v.w;
+        vd[4] += (double)__ldg(src1 + p);
     }
     // horizontal work item: 16 lanes per plane (14 segments of 8 outputs + 2 idle lanes), so that a
     // quarter-warp of a 128-bit access never mixes planes
@@ -751,9 +682,9 @@ k_fb_blur_solve(const float *__restrict__ M, int h, int w, float2 *__restrict__ 
     for (int y = y0; y < y_end; y++) {
         const bool more = y + 1 < y_end;
         if (more) {
-            const float *pin = src + fb_m_index(p_in), *pout = src + fb_m_index(p_out);
-#pragma unroll
-            for (int c = 0; c < 5; c++) { nin[c] = __ldg(pin + c * FB_MS); nout[c] = __ldg(pout + c * FB_MS); }
+            const float4 vi = __ldg(src4 + p_in), vo = __ldg(src4 + p_out);
+            nin[0] = vi.x; nin[1] = vi.y; nin[2] = vi.z; nin[3] = vi.w; nin[4] = __ldg(src1 + p_in);
+            nout[0] = vo.x; nout[1] = vo.y; nout[2] = vo.z; nout[3] = vo.w; nout[4] = __ldg(src1 + p_out);
             p_in += ((unsigned)yi < (unsigned)(h - 1)) ? (unsigned)w : 0u;     // replicate border: the row stops at 0 / h-1
             p_out += ((unsigned)yo < (unsigned)(h - 1)) ? (unsigned)w : 0u;
             yi++;
@@ -877,10 +808,6 @@ static void make_poly(PolyConst &pc)
     pc.ig11 = m[1][7]; pc.ig03 = m[0][9]; pc.ig33 = m[3][9]; pc.ig55 = m[5][11];
 }
 
-#ifdef VQA_AB
-#include "farneback_fused.cuh"
-#endif
-
 constexpr bool FB_DUAL_STREAMS = false;            // two-stream staggered schedule of a level (see run_farneback)
 
 int run_farneback(vqa_ctx *c, const uint8_t *gray, int npairs, int h, int w, double *mag_sum, float *flow_out)
@@ -897,14 +824,16 @@ int run_farneback(vqa_ctx *c, const uint8_t *gray, int npairs, int h, int w, dou
     }
     const size_t full = (size_t)h * w;
     VQA_BUF(c, I, float, "fb.I", full * nf);
-    VQA_BUF(c, R, float, "fb.R", full * 5 * nf);
-    const size_t m_pair = fb_m_pair_floats(h, w);                  // super-chunked planar M (level 0 is the largest)
-    VQA_BUF(c, M, float, "fb.M", m_pair * npairs);
+    // R (per frame) and M (per pair): per pixel one float4 (components 0..3) in the first 4/5 of the buffer and one float
+    // (component 4) behind it; frames / pairs are `level pixels` apart inside each part
+    VQA_BUF(c, Rbuf, float, "fb.R", full * 5 * nf);
+    VQA_BUF(c, Mbuf, float, "fb.M", full * 5 * npairs);
+    float4 *R4 = reinterpret_cast<float4 *>(Rbuf), *M4 = reinterpret_cast<float4 *>(Mbuf);
+    float *Rs = Rbuf + full * 4 * nf, *Ms = Mbuf + full * 4 * npairs;
     VQA_BUF(c, flowA, float2, "fb.flowA", full * npairs);
     VQA_BUF(c, flowB, float2, "fb.flowB", full * npairs);
 #ifdef VQA_AB
-    // development build only (the product build reads no environment): fused iteration and strip-height knobs
-    const bool fused = getenv("VQA_FB_FUSED") && atoi(getenv("VQA_FB_FUSED"));
+    // development build only (the product build reads no environment): strip-height, pair-group and two-stream knobs
     const int ms_h_cap = (getenv("VQA_MS_H") && atoi(getenv("VQA_MS_H")) >= 16) ? atoi(getenv("VQA_MS_H")) : MS_H;
     const int group = (getenv("VQA_FB_GROUP") && atoi(getenv("VQA_FB_GROUP")) >= 1) ? std::min(atoi(getenv("VQA_FB_GROUP")), npairs) : npairs;
     const bool dual = getenv("VQA_FB_DUAL") ? atoi(getenv("VQA_FB_DUAL")) != 0 : FB_DUAL_STREAMS;
@@ -959,31 +888,26 @@ int run_farneback(vqa_ctx *c, const uint8_t *gray, int npairs, int h, int w, dou
         VQA_BYTES(c, 24.0 * lw * lh * nf);
         const dim3 gE(cdiv(lw, PE_TW), cdiv(cdiv(lh, PE_TH), PE_STRIP), nf);
         VQA_CUDA(c, cudaFuncSetAttribute(k_fb_polyexp, cudaFuncAttributeMaxDynamicSharedMemorySize, PE_SMEM));
-        VQA_LAUNCH(c, k_fb_polyexp, gE, 256, PE_SMEM, I, lh, lw, pc, R);
-#ifdef VQA_AB
-        if (fused) {
-            const int rc = run_fused_level(c, R, flow, prev, ph, pw, lh, lw, npairs, k == levels, k == 0, mag_sum, flow_out != nullptr);
-            if (rc != VQA_OK) return rc;
-            float2 *t = prev; prev = flow; flow = t;
-            ph = lh; pw = lw;
-            continue;
-        }
-#endif
+        VQA_LAUNCH(c, k_fb_polyexp, gE, 256, PE_SMEM, I, lh, lw, pc, R4, Rs);
         // One group of pairs through the three iterations of the level, on the context's current stream.  `after_first`
         // is recorded behind the group's first kernel (the stagger of the two-stream schedule below).
         const size_t lpx = (size_t)lw * lh, ppx = (size_t)pw * ph;
-        auto run_group = [&](int g0, int gn, float *Mg, cudaEvent_t after_first) -> int {
-            const float *Rg = R + (size_t)g0 * 5 * lpx;
+        auto run_group = [&](int g0, int gn, size_t m0, cudaEvent_t after_first) -> int {
+            // frame g0 of R, pair m0 of M (M is scratch: groups of the sequential schedule reuse pair 0 onwards), pair g0 of the flows
+            const float4 *Rg4 = R4 + (size_t)g0 * lpx;
+            const float *Rgs = Rs + (size_t)g0 * lpx;
+            float4 *Mg4 = M4 + m0 * lpx;
+            float *Mgs = Ms + m0 * lpx;
             float2 *fg = flow + (size_t)g0 * lpx;
             const float2 *pg = prev + (size_t)g0 * ppx;
             const dim3 gPg(gn, cdiv(lw, 32), cdiv(lh, 8));
             // first UpdateMatrices of the level: zero flow at the coarsest level, else the coarser flow up-sampled on the fly
             if (k == levels) {
                 VQA_BYTES(c, 60.0 * lpx * gn);
-                VQA_LAUNCH(c, k_fb_matrices<2>, gPg, 256, 0, Rg, fg, lh, lw, Mg, pg, ph, pw);
+                VQA_LAUNCH(c, k_fb_matrices<2>, gPg, 256, 0, Rg4, Rgs, fg, lh, lw, Mg4, Mgs, pg, ph, pw);
             } else {
                 VQA_BYTES(c, (60.0 * lpx + 8.0 * ppx) * gn);
-                VQA_LAUNCH(c, k_fb_matrices<1>, gPg, 256, 0, Rg, fg, lh, lw, Mg, pg, ph, pw);
+                VQA_LAUNCH(c, k_fb_matrices<1>, gPg, 256, 0, Rg4, Rgs, fg, lh, lw, Mg4, Mgs, pg, ph, pw);
             }
             if (after_first) VQA_CUDA(c, cudaEventRecord(after_first, c->stream));
             // rows per block of the marching blur: long strips amortise the 15-row warm-up, but the small
@@ -1002,11 +926,10 @@ int run_farneback(vqa_ctx *c, const uint8_t *gray, int npairs, int h, int w, dou
                 double *ms = last ? mag_sum + g0 : (double *)nullptr;
                 const int wf = (!last || flow_out) ? 1 : 0;
                 VQA_BYTES(c, 28.0 * lpx * gn);
-                VQA_LAUNCH(c, k_fb_blur_solve, gB, MS_W, 0, Mg, lh, lw, fg, rows_pb, ms, wf);
+                VQA_LAUNCH(c, k_fb_blur_solve, gB, MS_W, 0, Mg4, Mgs, lh, lw, fg, rows_pb, ms, wf);
                 if (it < 2) {
                     VQA_BYTES(c, 68.0 * lpx * gn);
-                    if ((lw & 3) == 0) VQA_LAUNCH(c, k_fb_matrices_t4, dim3(gn, cdiv(lw, 128), cdiv(lh, 8)), 256, 0, Rg, fg, lh, lw, Mg);
-                    else VQA_LAUNCH(c, k_fb_matrices<0>, gPg, 256, 0, Rg, fg, lh, lw, Mg, pg, ph, pw);
+                    VQA_LAUNCH(c, k_fb_matrices<0>, gPg, 256, 0, Rg4, Rgs, fg, lh, lw, Mg4, Mgs, pg, ph, pw);
                 }
             }
             return VQA_OK;
@@ -1020,11 +943,11 @@ int run_farneback(vqa_ctx *c, const uint8_t *gray, int npairs, int h, int w, dou
             cudaStream_t main_stream = c->stream;
             VQA_CUDA(c, cudaEventRecord(c->ev_fb_fork, main_stream));
             VQA_CUDA(c, cudaStreamWaitEvent(c->fb_stream, c->ev_fb_fork, 0));
-            if (int rc = run_group(0, ga, M, c->ev_fb_stagger)) return rc;
+            if (int rc = run_group(0, ga, 0, c->ev_fb_stagger)) return rc;
             {
                 c->stream = c->fb_stream;
                 cudaError_t e = cudaStreamWaitEvent(c->fb_stream, c->ev_fb_stagger, 0);
-                int rc = e == cudaSuccess ? run_group(ga, gb, M + (size_t)ga * m_pair, nullptr) : VQA_E_CUDA;
+                int rc = e == cudaSuccess ? run_group(ga, gb, (size_t)ga, nullptr) : VQA_E_CUDA;
                 if (rc == VQA_OK && cudaEventRecord(c->ev_fb_join, c->fb_stream) != cudaSuccess) rc = VQA_E_CUDA;
                 c->stream = main_stream;
                 if (rc) return rc == VQA_E_CUDA ? set_err(c, VQA_E_CUDA, "two-stream Farneback schedule: %s", cudaGetErrorString(cudaGetLastError())) : rc;
@@ -1035,7 +958,7 @@ int run_farneback(vqa_ctx *c, const uint8_t *gray, int npairs, int h, int w, dou
             // cut the chunk into groups whose M field stays in L2 between its writer and its reader: measured negative,
             // profiles/r02_notes.md 3)
             for (int g0 = 0; g0 < npairs; g0 += group)
-                if (int rc = run_group(g0, std::min(group, npairs - g0), M, nullptr)) return rc;
+                if (int rc = run_group(g0, std::min(group, npairs - g0), 0, nullptr)) return rc;
         }
         float2 *t = prev; prev = flow; flow = t;
         ph = lh; pw = lw;
