@@ -471,9 +471,19 @@ k_fb_polyexp(const float *__restrict__ I, int h, int w, PolyConst pc, float4 *__
                 float4 *d4 = R4 + o0;
                 float *d1 = Rs + o0;
                 const bool vec = (w & 3) == 0 && gx0 + 4 <= w;          // arrays are 256-byte aligned, w % 4 == 0 keeps rows aligned
+                if (vec) {
+                    // the four pixels of this thread are 64 contiguous bytes: two 256-bit stores (sm_100), each a full
+                    // 32-byte sector (four 128-bit stores with the lanes 64 bytes apart touched every sector twice)
 #pragma unroll
-                for (int j = 0; j < 4; j++)
-                    if (vec || gx0 + j < w) d4[j] = make_float4(o[0][j], o[1][j], o[2][j], o[3][j]);
+                    for (int j = 0; j < 4; j += 2)
+                        asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(d4 + j), "f"(o[0][j]), "f"(o[1][j]),
+                                     "f"(o[2][j]), "f"(o[3][j]), "f"(o[0][j + 1]), "f"(o[1][j + 1]), "f"(o[2][j + 1]), "f"(o[3][j + 1])
+                                     : "memory");
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        if (gx0 + j < w) d4[j] = make_float4(o[0][j], o[1][j], o[2][j], o[3][j]);
+                }
                 if (vec) *reinterpret_cast<float4 *>(d1) = make_float4(o[4][0], o[4][1], o[4][2], o[4][3]);
                 else
                     for (int j = 0; j < 4; j++)
@@ -637,9 +647,15 @@ constexpr int MS_VP = 144;
 //     uses double here too); float-float pairs updated with TwoSum measured 8 % slower, evaluating the
 //     next UpdateMatrices in the epilogue 7 % slower (profiles/r01_notes.md; both variants removed).
 // The new flow is stored; on the last iteration of level 0 the caller may ask for sum |flow| instead.
+// NEXT 1 (iterations 0 and 1 of a level): the new flow never leaves the registers -- UpdateMatrices of the NEXT iteration is
+// pointwise in the pixel, so it is evaluated right here from R and the fresh flow and written to the other M buffer: the
+// separate UpdateMatrices launch, the flow store and the flow load of that iteration disappear (round 1 measured this 7 %
+// slower with planar R: 20 scalar gathers exposed once per row; with the float4 + float layout the taps are 8 loads).
+template <int NEXT>
 __global__ void __launch_bounds__(MS_W)
 k_fb_blur_solve(const float4 *__restrict__ M4, const float *__restrict__ Ms, int h, int w, float2 *__restrict__ flow,
-                int rows_per_block, double *__restrict__ mag_sum, int write_flow)
+                int rows_per_block, double *__restrict__ mag_sum, int write_flow, const float4 *__restrict__ R4,
+                const float *__restrict__ Rs, float4 *__restrict__ Mn4, float *__restrict__ Mns)
 {
     __shared__ __align__(16) float row[5][MS_VP];
     __shared__ __align__(16) float hs[5][MS_VP];
@@ -673,7 +689,8 @@ k_fb_blur_solve(const float4 *__restrict__ M4, const float *__restrict__ Ms, int
     float *hout0 = &hs[hwork ? hc : 0][ms_sw((hwork ? hseg : 0) * MS_SEG + 8)];
     float *hout1 = &hs[hwork ? hc : 0][ms_sw((hwork ? hseg : 0) * MS_SEG + 12)];
     const float *my_hs = &hs[0][ms_sw(t)];
-    float2 *fout = flow + (size_t)pair * plane + (size_t)y0 * w + (has_out ? gxo : 0);
+    float2 *fout = NEXT ? nullptr : flow + (size_t)pair * plane + (size_t)y0 * w + (has_out ? gxo : 0);
+    size_t onext = (size_t)pair * plane + (size_t)y0 * w + (has_out ? gxo : 0);     // NEXT: this thread's pixel in R0 / the next M
     // rows entering (yi) / leaving (yo) the 15-row window when the output row advances to y+1
     int yi = y0 + 1 + MS_R, yo = y0 - MS_R;
     unsigned p_in = (unsigned)(clampi(yi, 0, h - 1) * w + gx), p_out = (unsigned)(clampi(yo, 0, h - 1) * w + gx);   // linear pixel indices
@@ -681,6 +698,12 @@ k_fb_blur_solve(const float4 *__restrict__ M4, const float *__restrict__ Ms, int
     double mag_acc = 0;
     for (int y = y0; y < y_end; y++) {
         const bool more = y + 1 < y_end;
+        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+        float q4 = 0.f;
+        if (NEXT && has_out) {                                      // R of the previous frame at the output pixel: no dependence on the flow
+            q = __ldg(R4 + onext);
+            q4 = __ldg(Rs + onext);
+        }
         if (more) {
             const float4 vi = __ldg(src4 + p_in), vo = __ldg(src4 + p_out);
             nin[0] = vi.x; nin[1] = vi.y; nin[2] = vi.z; nin[3] = vi.w; nin[4] = __ldg(src1 + p_in);
@@ -732,18 +755,26 @@ k_fb_blur_solve(const float4 *__restrict__ M4, const float *__restrict__ Ms, int
             float2 o;
             o.x = __fmul_rn(__fmul_rn(nx, k2), idet);
             o.y = __fmul_rn(__fmul_rn(ny, k2), idet);
-            if (write_flow) *fout = o;
-            // last iteration of level 0: the flow field itself is not needed any more, only
-            // sum |flow| (cartToPolar magnitude, complexity_metrics.py:342-343)
-            if (mag_sum) mag_acc += (double)sqrtf(__fadd_rn(__fmul_rn(o.x, o.x), __fmul_rn(o.y, o.y)));
+            if (NEXT) {
+                float m[5];
+                fb_matrix_core(q, q4, R4 + (size_t)(pair + 1) * plane, Rs + (size_t)(pair + 1) * plane, gxo, y, h, w, o, m);
+                Mn4[onext] = make_float4(m[0], m[1], m[2], m[3]);
+                Mns[onext] = m[4];
+            } else {
+                if (write_flow) *fout = o;
+                // last iteration of level 0: the flow field itself is not needed any more, only
+                // sum |flow| (cartToPolar magnitude, complexity_metrics.py:342-343)
+                if (mag_sum) mag_acc += (double)sqrtf(__fadd_rn(__fmul_rn(o.x, o.x), __fmul_rn(o.y, o.y)));
+            }
         }
-        fout += w;
+        if (NEXT) onext += w;
+        else fout += w;
         if (more) {
 #pragma unroll
             for (int c = 0; c < 5; c++) vd[c] = (vd[c] + (double)nin[c]) - (double)nout[c];
         }
     }
-    if (mag_sum) {
+    if (!NEXT && mag_sum) {
         __shared__ double red[MS_W / 32];
         mag_acc = warp_sum(mag_acc);
         __syncthreads();
@@ -809,6 +840,7 @@ static void make_poly(PolyConst &pc)
 }
 
 constexpr bool FB_DUAL_STREAMS = false;            // two-stream staggered schedule of a level (see run_farneback)
+constexpr bool FB_FUSE_NEXT = false;               // iterations 0 and 1 of a level: the blur evaluates the next UpdateMatrices itself
 
 int run_farneback(vqa_ctx *c, const uint8_t *gray, int npairs, int h, int w, double *mag_sum, float *flow_out)
 {
@@ -828,8 +860,8 @@ int run_farneback(vqa_ctx *c, const uint8_t *gray, int npairs, int h, int w, dou
     // (component 4) behind it; frames / pairs are `level pixels` apart inside each part
     VQA_BUF(c, Rbuf, float, "fb.R", full * 5 * nf);
     VQA_BUF(c, Mbuf, float, "fb.M", full * 5 * npairs);
-    float4 *R4 = reinterpret_cast<float4 *>(Rbuf), *M4 = reinterpret_cast<float4 *>(Mbuf);
-    float *Rs = Rbuf + full * 4 * nf, *Ms = Mbuf + full * 4 * npairs;
+    float4 *R4 = reinterpret_cast<float4 *>(Rbuf), *M4 = reinterpret_cast<float4 *>(Mbuf), *N4 = nullptr;
+    float *Rs = Rbuf + full * 4 * nf, *Ms = Mbuf + full * 4 * npairs, *Ns = nullptr;
     VQA_BUF(c, flowA, float2, "fb.flowA", full * npairs);
     VQA_BUF(c, flowB, float2, "fb.flowB", full * npairs);
 #ifdef VQA_AB
@@ -837,11 +869,18 @@ int run_farneback(vqa_ctx *c, const uint8_t *gray, int npairs, int h, int w, dou
     const int ms_h_cap = (getenv("VQA_MS_H") && atoi(getenv("VQA_MS_H")) >= 16) ? atoi(getenv("VQA_MS_H")) : MS_H;
     const int group = (getenv("VQA_FB_GROUP") && atoi(getenv("VQA_FB_GROUP")) >= 1) ? std::min(atoi(getenv("VQA_FB_GROUP")), npairs) : npairs;
     const bool dual = getenv("VQA_FB_DUAL") ? atoi(getenv("VQA_FB_DUAL")) != 0 : FB_DUAL_STREAMS;
+    const bool fuse_next = getenv("VQA_FB_NEXT") ? atoi(getenv("VQA_FB_NEXT")) != 0 : FB_FUSE_NEXT;
 #else
+    constexpr bool fuse_next = FB_FUSE_NEXT;
     constexpr bool dual = FB_DUAL_STREAMS;
     constexpr int ms_h_cap = MS_H;
     const int group = npairs;
 #endif
+    if (fuse_next) {                                                 // the blur that also evaluates the next UpdateMatrices writes the other M buffer
+        VQA_BUF(c, Mbuf2, float, "fb.M2", full * 5 * npairs);
+        N4 = reinterpret_cast<float4 *>(Mbuf2);
+        Ns = Mbuf2 + full * 4 * npairs;
+    }
     PolyConst pc;
     make_poly(pc);
     VQA_CUDA(c, cudaMemsetAsync(mag_sum, 0, sizeof(double) * (size_t)npairs, c->stream));
@@ -921,12 +960,23 @@ int run_farneback(vqa_ctx *c, const uint8_t *gray, int npairs, int h, int w, dou
                 if (rows_pb > ms_h_cap) rows_pb = ms_h_cap;
             }
             const dim3 gB(cdiv(lw, MS_OUT), cdiv(lh, rows_pb), gn);
+            float4 *Ng4 = N4 + m0 * lpx;
+            float *Ngs = Ns + m0 * lpx;
             for (int it = 0; it < 3; it++) {
                 const bool last = (k == 0 && it == 2);
                 double *ms = last ? mag_sum + g0 : (double *)nullptr;
                 const int wf = (!last || flow_out) ? 1 : 0;
+                if (it < 2 && fuse_next) {
+                    // blur + solve + the next iteration's UpdateMatrices: M 20 + R0 20 + R1 20 read, M' 20 written
+                    VQA_BYTES(c, 80.0 * lpx * gn);
+                    VQA_LAUNCH(c, k_fb_blur_solve<1>, gB, MS_W, 0, Mg4, Mgs, lh, lw, fg, rows_pb, (double *)nullptr, 0, Rg4, Rgs, Ng4, Ngs);
+                    std::swap(Mg4, Ng4);
+                    std::swap(Mgs, Ngs);
+                    continue;
+                }
                 VQA_BYTES(c, 28.0 * lpx * gn);
-                VQA_LAUNCH(c, k_fb_blur_solve, gB, MS_W, 0, Mg4, Mgs, lh, lw, fg, rows_pb, ms, wf);
+                VQA_LAUNCH(c, k_fb_blur_solve<0>, gB, MS_W, 0, Mg4, Mgs, lh, lw, fg, rows_pb, ms, wf, (const float4 *)nullptr,
+                           (const float *)nullptr, (float4 *)nullptr, (float *)nullptr);
                 if (it < 2) {
                     VQA_BYTES(c, 68.0 * lpx * gn);
                     VQA_LAUNCH(c, k_fb_matrices<0>, gPg, 256, 0, Rg4, Rgs, fg, lh, lw, Mg4, Mgs, pg, ph, pw);
