@@ -120,6 +120,8 @@ using namespace vqa;
 
 extern "C" {
 
+static constexpr bool SIDE_STREAM_HIGH_PRIORITY = false;
+
 int vqa_abi_version(void) { return VQA_ABI_VERSION; }
 
 int vqa_init(int device, vqa_ctx **out)
@@ -140,9 +142,19 @@ int vqa_init(int device, vqa_ctx **out)
     vqa_ctx *c = new vqa_ctx();
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
+    // The side stream (Canny / ORB / DCT of a chunk) can be given the HIGHER priority: its blocks are then dispatched as
+    // soon as SM slots free up and run next to the Farneback kernel in flight (ALU / tensor work next to memory-bound work);
+    // at equal priority the block scheduler drains the older kernel first and the side kernels only fill its tail.
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+#ifdef VQA_AB
+    const bool side_high = getenv("VQA_SIDE_PRIO") ? atoi(getenv("VQA_SIDE_PRIO")) != 0 : SIDE_STREAM_HIGH_PRIORITY;
+#else
+    constexpr bool side_high = SIDE_STREAM_HIGH_PRIORITY;
+#endif
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&c->side_stream, cudaStreamNonBlocking, side_high ? prio_hi : prio_lo) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->fb_stream, cudaStreamNonBlocking) != cudaSuccess ||

@@ -24,5 +24,6 @@ cut -c1-600 $O/r02_${T}_ref_c1.json; cut -c1-400 $O/r02_${T}_ref_c2.json
 VQA_PROF_REPORT=$O/r02_${T}_step_report.json timeout 300 python tools/profile_step.py 24 > $O/prof_plain.log 2>&1 || tail -5 $O/prof_plain.log
 timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --profile-from-start off -c 400 --csv \
     --log-file $O/r02_${T}_ncu_launches_step24.csv python tools/profile_step.py 24 > $O/r02_${T}_ncu_launches.log 2>&1; echo "ncu rc=$?"
-python tools/traffic_from_csv.py $O/r02_${T}_ncu_launches_step24.csv $O/r02_${T}_step_report.json r02_${T}_ncu_launches_step24.csv | tee $O/r02_${T}_traffic.txt
+python tools/traffic_from_csv.py $O/r02_${T}_ncu_launches_step24.csv $O/r02_${T}_step_report.json r02_${T}_ncu_launches_step24.csv | tee $O/r02_${T}_traffic.txt | head -14
 cp profiles/ncu_traffic.json $O/r02_${T}_ncu_traffic.json
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/r02_${T}_smoke.log 2>&1; echo "smoke rc=$?"; tail -1 $O/r02_${T}_smoke.log
