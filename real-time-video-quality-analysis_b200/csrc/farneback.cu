@@ -960,12 +960,15 @@ int run_farneback(vqa_ctx *c, const uint8_t *gray, int npairs, int h, int w, dou
                 if (rows_pb > ms_h_cap) rows_pb = ms_h_cap;
             }
             const dim3 gB(cdiv(lw, MS_OUT), cdiv(lh, rows_pb), gn);
+#ifdef VQA_AB
             float4 *Ng4 = N4 + m0 * lpx;
             float *Ngs = Ns + m0 * lpx;
+#endif
             for (int it = 0; it < 3; it++) {
                 const bool last = (k == 0 && it == 2);
                 double *ms = last ? mag_sum + g0 : (double *)nullptr;
                 const int wf = (!last || flow_out) ? 1 : 0;
+#ifdef VQA_AB                                                        // the losing variant is compiled into the development build only
                 if (it < 2 && fuse_next) {
                     // blur + solve + the next iteration's UpdateMatrices: M 20 + R0 20 + R1 20 read, M' 20 written
                     VQA_BYTES(c, 80.0 * lpx * gn);
@@ -974,6 +977,7 @@ int run_farneback(vqa_ctx *c, const uint8_t *gray, int npairs, int h, int w, dou
                     std::swap(Mgs, Ngs);
                     continue;
                 }
+#endif
                 VQA_BYTES(c, 28.0 * lpx * gn);
                 VQA_LAUNCH(c, k_fb_blur_solve<0>, gB, MS_W, 0, Mg4, Mgs, lh, lw, fg, rows_pb, ms, wf, (const float4 *)nullptr,
                            (const float *)nullptr, (float4 *)nullptr, (float *)nullptr);

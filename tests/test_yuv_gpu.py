@@ -68,7 +68,9 @@ def test_yuv2bgr_odd_sizes_are_refused(ctx):
 
 
 # ------------------------------------------------------------------ one upload, both halves
-@pytest.mark.parametrize("h,w,rw,rh", [(72, 96, 64, 64), (144, 192, 192, 144), (70, 102, 64, 64)])
+# (144, 192) and (72, 96) at native resolution take the fused ingest (planes -> gray + histograms, BGR only in registers, histogram
+# moments for the DCT); (70, 102) at native resolution cannot (w % 8 != 0) and (.., 64, 64) must not: both go through BGR frames
+@pytest.mark.parametrize("h,w,rw,rh", [(72, 96, 64, 64), (144, 192, 192, 144), (72, 96, 96, 72), (70, 102, 64, 64), (70, 102, 102, 70)])
 def test_analyze_clip_yuv420_equals_the_two_halves(ctx, synth, h, w, rw, rh):
     import torch
     n = 7
