@@ -372,13 +372,22 @@ constexpr int PE_P = 76;                         // tile pitch (64 + 2*5 = 74, p
 constexpr int PE_STRIP = 4;
 constexpr int PE_SMEM = (2 * (PE_TH + 2 * PE_R) + 3 * PE_TH) * PE_P * (int)sizeof(float);
 
+// One warp per tile row, lanes over the columns (three column groups of 32: 76 = 32 + 32 + 12): the clamped source column of a
+// lane is computed once per tile and the row pointer once per row, so an element costs an add and the copy (the flat
+// `i / PE_P` loop spent ~25 instructions per element on division, clamps and 64-bit address arithmetic: 15 % of the kernel).
 __device__ __forceinline__ void pe_load_tile(float (*tile)[PE_P], const float *__restrict__ src, int h, int w, int tx0, int ty0, int tid)
 {
-    for (int i = tid; i < (PE_TH + 2 * PE_R) * PE_P; i += 256) {
-        const int y = i / PE_P, x = i - y * PE_P;
-        const float *g = src + (size_t)clampi(ty0 - PE_R + y, 0, h - 1) * w + clampi(tx0 - PE_R + x, 0, w - 1);
-        const unsigned dst = (unsigned)__cvta_generic_to_shared(&tile[y][x]);
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(g) : "memory");
+    const int lane = tid & 31, wrp = tid >> 5;
+    int cx[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) cx[k] = clampi(tx0 - PE_R + lane + 32 * k, 0, w - 1);
+    for (int y = wrp; y < PE_TH + 2 * PE_R; y += 8) {
+        const float *g = src + (size_t)clampi(ty0 - PE_R + y, 0, h - 1) * w;
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(&tile[y][lane]);
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+            if (lane + 32 * k < PE_P)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 128u * k), "l"(g + cx[k]) : "memory");
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
@@ -633,6 +642,31 @@ constexpr int MS_W = 128, MS_OUT = 112, MS_R = 7, MS_H = 96, MS_SEG = 8;
 __device__ __forceinline__ int ms_sw(int i) { return i + ((i >> 5) << 2); }
 constexpr int MS_VP = 144;
 
+// Shared-memory accessors on 32-bit shared-window addresses held in registers.  The swizzled addresses of a thread are loop
+// invariants, but written as C++ pointers the compiler re-derived them from threadIdx inside the row loop (shift / mask / add
+// chains, ~25 of the kernel's 211 instructions per pixel, to stay at 56 registers); `opaque` hides their provenance so they are
+// computed once and kept.
+__device__ __forceinline__ uint32_t ms_opaque(uint32_t a) { asm volatile("" : "+r"(a)); return a; }
+template <int OFF>
+__device__ __forceinline__ void ms_sts(uint32_t a, float v) { asm volatile("st.shared.f32 [%0+%1], %2;" ::"r"(a), "n"(OFF), "f"(v) : "memory"); }
+template <int OFF>
+__device__ __forceinline__ float ms_lds(uint32_t a)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(a), "n"(OFF) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 ms_lds128(uint32_t a)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void ms_sts128(uint32_t a, float4 v)
+{
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 // FarnebackUpdateFlow_Blur, column-marching (see above).  On B200 this kernel is bound by warp
 // instruction ISSUE (ncu: issue slots 78 % busy, 3 eligible warps per cycle; DRAM 46 %, L1 70 %), so
 // the design minimises instructions per output, in this order of discovery (profiles/r01_notes.md):
@@ -681,14 +715,13 @@ k_fb_blur_solve(const float4 *__restrict__ M4, const float *__restrict__ Ms, int
     const bool hwork = t < 80 && hseg < 14;
     const int ox = t - 8, gxo = sx0 + ox;                           // output column of this thread
     const bool has_out = ox >= 0 && ox < MS_OUT && gxo < w;
-    float *my_row = &row[0][ms_sw(t)];
-    const float *hrow = row[hwork ? hc : 0];
-    int hoff[6];
+    const uint32_t row_a = (uint32_t)__cvta_generic_to_shared(&row[0][0]), hs_a = (uint32_t)__cvta_generic_to_shared(&hs[0][0]);
+    const uint32_t my_row = ms_opaque(row_a + 4u * ms_sw(t)), my_hs = ms_opaque(hs_a + 4u * ms_sw(t));
+    const int hplane = (hwork ? hc : 0) * MS_VP, hcol = (hwork ? hseg : 0) * MS_SEG;
+    uint32_t hin[6];
 #pragma unroll
-    for (int j = 0; j < 6; j++) hoff[j] = ms_sw((hwork ? hseg : 0) * MS_SEG + 4 * j);
-    float *hout0 = &hs[hwork ? hc : 0][ms_sw((hwork ? hseg : 0) * MS_SEG + 8)];
-    float *hout1 = &hs[hwork ? hc : 0][ms_sw((hwork ? hseg : 0) * MS_SEG + 12)];
-    const float *my_hs = &hs[0][ms_sw(t)];
+    for (int j = 0; j < 6; j++) hin[j] = ms_opaque(row_a + 4u * (hplane + ms_sw(hcol + 4 * j)));
+    const uint32_t hout0 = ms_opaque(hs_a + 4u * (hplane + ms_sw(hcol + 8))), hout1 = ms_opaque(hs_a + 4u * (hplane + ms_sw(hcol + 12)));
     float2 *fout = NEXT ? nullptr : flow + (size_t)pair * plane + (size_t)y0 * w + (has_out ? gxo : 0);
     size_t onext = (size_t)pair * plane + (size_t)y0 * w + (has_out ? gxo : 0);     // NEXT: this thread's pixel in R0 / the next M
     // rows entering (yi) / leaving (yo) the 15-row window when the output row advances to y+1
@@ -713,15 +746,18 @@ k_fb_blur_solve(const float4 *__restrict__ M4, const float *__restrict__ Ms, int
             yi++;
             yo++;
         }
-#pragma unroll
-        for (int c = 0; c < 5; c++) my_row[c * MS_VP] = (float)vd[c];
+        ms_sts<0>(my_row, (float)vd[0]);
+        ms_sts<4 * MS_VP>(my_row, (float)vd[1]);
+        ms_sts<8 * MS_VP>(my_row, (float)vd[2]);
+        ms_sts<12 * MS_VP>(my_row, (float)vd[3]);
+        ms_sts<16 * MS_VP>(my_row, (float)vd[4]);
         __syncthreads();
         if (hwork) {
             // p[k] = column 8s + k; output o of the segment sums columns 8s+o+1 .. 8s+o+15
             float p[24];
 #pragma unroll
             for (int j = 0; j < 6; j++) {
-                const float4 v = *reinterpret_cast<const float4 *>(hrow + hoff[j]);
+                const float4 v = ms_lds128(hin[j]);
                 p[4 * j] = v.x; p[4 * j + 1] = v.y; p[4 * j + 2] = v.z; p[4 * j + 3] = v.w;
             }
             const float core = ((p[8] + p[9]) + (p[10] + p[11])) + ((p[12] + p[13]) + (p[14] + p[15]));
@@ -735,8 +771,8 @@ k_fb_blur_solve(const float4 *__restrict__ M4, const float *__restrict__ Ms, int
             float o8[MS_SEG];
 #pragma unroll
             for (int j = 0; j < MS_SEG; j++) o8[j] = (core + L[j]) + R[j];
-            *reinterpret_cast<float4 *>(hout0) = make_float4(o8[0], o8[1], o8[2], o8[3]);
-            *reinterpret_cast<float4 *>(hout1) = make_float4(o8[4], o8[5], o8[6], o8[7]);
+            ms_sts128(hout0, make_float4(o8[0], o8[1], o8[2], o8[3]));
+            ms_sts128(hout1, make_float4(o8[4], o8[5], o8[6], o8[7]));
         }
         __syncthreads();
         if (has_out) {
@@ -745,7 +781,8 @@ k_fb_blur_solve(const float4 *__restrict__ M4, const float *__restrict__ Ms, int
             // formed in float with the product error recovered by FMA (w = c*d, e = fma(-c, d, w),
             // a*b - c*d = fma(a, b, -w) + e: below 2 ulp even under cancellation), so the XU pipe sees
             // one reciprocal instead of ten float<->double conversions per output
-            const float s11 = my_hs[0], s12 = my_hs[MS_VP], s22 = my_hs[2 * MS_VP], t1 = my_hs[3 * MS_VP], t2 = my_hs[4 * MS_VP];
+            const float s11 = ms_lds<0>(my_hs), s12 = ms_lds<4 * MS_VP>(my_hs), s22 = ms_lds<8 * MS_VP>(my_hs),
+                        t1 = ms_lds<12 * MS_VP>(my_hs), t2 = ms_lds<16 * MS_VP>(my_hs);
             const float k2 = 1.f / (225.f * 225.f);
             const float w0 = __fmul_rn(s12, s12), w1 = __fmul_rn(s12, t1), w2 = __fmul_rn(s12, t2);
             const float det = __fmaf_rn(__fadd_rn(__fmaf_rn(s11, s22, -w0), __fmaf_rn(-s12, s12, w0)), k2, 1e-3f);
