@@ -369,7 +369,7 @@ constexpr int PE_P = 76;                         // tile pitch (64 + 2*5 = 74, p
 // A block walks PE_STRIP vertically adjacent tiles; the pixel tile is double-buffered and filled with
 // 4-byte cp.async (any alignment, border clamp in the address), so the loads of tile k+1 fly while
 // tile k is computed (the synchronous version sat 63 % of its stall samples on the tile load).
-constexpr int PE_STRIP = 4;
+constexpr int PE_STRIP = 4, PE_VR = 4;
 constexpr int PE_SMEM = (2 * (PE_TH + 2 * PE_R) + 3 * PE_TH) * PE_P * (int)sizeof(float);
 
 // One warp per tile row, lanes over the columns (three column groups of 32: 76 = 32 + 32 + 12): the clamped source column of a
@@ -416,27 +416,29 @@ k_fb_polyexp(const float *__restrict__ I, int h, int w, PolyConst pc, float4 *__
             asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         __syncthreads();
-        for (int i = tid; i < PE_TH * (PE_P / 4); i += 256) {
-            const int y = i / (PE_P / 4), x = (i - y * (PE_P / 4)) * 4;
-            const float4 c4 = *reinterpret_cast<const float4 *>(&T[y + PE_R][x]);
-            float t0[4] = {c4.x * pc.g[PE_R], c4.y * pc.g[PE_R], c4.z * pc.g[PE_R], c4.w * pc.g[PE_R]};
-            float t1[4] = {0.f, 0.f, 0.f, 0.f}, t2[4] = {0.f, 0.f, 0.f, 0.f};
+        // vertical pass: a work item owns ONE column and PE_VR consecutive rows, so the 2 * PE_R + PE_VR tile values it needs are
+        // read once (14 loads for 4 outputs; one row per item read 11 values per output: the kernel is bound by the L1 data
+        // pipe, 86 %, and this pass was 55 % of its shared-memory wavefronts).  Same expressions per output as before.
+        for (int i = tid; i < (PE_TH / PE_VR) * PE_P; i += 256) {
+            const int yg = i / PE_P, x = i - yg * PE_P, y0 = yg * PE_VR;
+            float r[PE_VR + 2 * PE_R];
 #pragma unroll
-            for (int k = 1; k <= PE_R; k++) {
-                const float4 a4 = *reinterpret_cast<const float4 *>(&T[y + PE_R - k][x]);
-                const float4 b4 = *reinterpret_cast<const float4 *>(&T[y + PE_R + k][x]);
-                const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+            for (int q = 0; q < PE_VR + 2 * PE_R; q++) r[q] = T[y0 + q][x];
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const float p = a[j] + b[j];
-                    t0[j] = t0[j] + pc.g[PE_R + k] * p;
-                    t1[j] = t1[j] + pc.xg[PE_R + k] * (b[j] - a[j]);
-                    t2[j] = t2[j] + pc.xxg[PE_R + k] * p;
+            for (int o = 0; o < PE_VR; o++) {
+                float t0 = r[o + PE_R] * pc.g[PE_R], t1 = 0.f, t2 = 0.f;
+#pragma unroll
+                for (int k = 1; k <= PE_R; k++) {
+                    const float a = r[o + PE_R - k], b = r[o + PE_R + k];
+                    const float p = a + b;
+                    t0 = t0 + pc.g[PE_R + k] * p;
+                    t1 = t1 + pc.xg[PE_R + k] * (b - a);
+                    t2 = t2 + pc.xxg[PE_R + k] * p;
                 }
+                v0[y0 + o][x] = t0;
+                v1[y0 + o][x] = t1;
+                v2[y0 + o][x] = t2;
             }
-            *reinterpret_cast<float4 *>(&v0[y][x]) = make_float4(t0[0], t0[1], t0[2], t0[3]);
-            *reinterpret_cast<float4 *>(&v1[y][x]) = make_float4(t1[0], t1[1], t1[2], t1[3]);
-            *reinterpret_cast<float4 *>(&v2[y][x]) = make_float4(t2[0], t2[1], t2[2], t2[3]);
         }
         __syncthreads();
         if (gx0 < w) {
