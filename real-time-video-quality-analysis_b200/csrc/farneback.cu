@@ -625,7 +625,7 @@ k_fb_matrices(const float4 *__restrict__ R4, const float *__restrict__ Rs, const
     Ms[o] = m[4];
 }
 
-constexpr int MS_W = 128, MS_OUT = 112, MS_R = 7, MS_H = 96, MS_SEG = 8;
+constexpr int MS_W = 128, MS_OUT = 112, MS_R = 7, MS_H = 96, MS_SEG = 8, MS_PF = 6;
 
 // FarnebackUpdateFlow_Blur: 15x15 replicate-border box mean of the 5 planes of M, then the 2x2 solve.
 // "Column marching": a block owns a strip of 112 output columns (+8 halo columns each side = 128
@@ -738,6 +738,13 @@ k_fb_blur_solve(const float4 *__restrict__ M4, const float *__restrict__ Ms, int
         if (NEXT && has_out) {                                      // R of the previous frame at the output pixel: no dependence on the flow
             q = __ldg(R4 + onext);
             q4 = __ldg(Rs + onext);
+        }
+        if (MS_PF > 0 && y + MS_PF < y_end) {
+            // the row that enters the window MS_PF rows from now -> L2 (its first touch: a DRAM access whose latency otherwise
+            // sets the duration of a row iteration; the row that leaves was read 15 rows earlier and mostly still is in L2)
+            const unsigned pf = (unsigned)(min(y + MS_PF + MS_R, h - 1) * w + gx);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(src4 + pf));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(src1 + pf));
         }
         if (more) {
             const float4 vi = __ldg(src4 + p_in), vo = __ldg(src4 + p_out);
