@@ -8,6 +8,8 @@
 
 #include <algorithm>
 
+#include <functional>
+
 #include <nvtx3/nvToolsExt.h>
 
 #include "vqa_common.cuh"
@@ -641,11 +643,14 @@ int complexity_body(vqa_ctx *c, const uint8_t *bgr, int n, int h, int w, size_t 
         // latency / tensor-bound kernels of this chain fill the gaps of the DRAM- and LSU-bound flow
         // kernels (joined at the end of the chunk)
         const bool fork = use_side && !c->ktiming && want_motion && (want_edge || want_orb || want_dct);
-        if (fork) {
-            VQA_CUDA(c, cudaEventRecord(c->ev_fork, c->stream));
-            VQA_CUDA(c, cudaStreamWaitEvent(c->side_stream, c->ev_fork, 0));
-        }
-        {
+        // the side chain as a callable: launched here (default) or, in the development build's VQA_SIDE_AT_L0 schedule, from
+        // inside run_farneback right before the first level-0 UpdateMatrices (the DRAM-bound kernels of the chain)
+        auto side_chain = [&]() -> int {
+            int rc = VQA_OK;
+            if (fork) {
+                VQA_CUDA(c, cudaEventRecord(c->ev_fork, c->stream));
+                VQA_CUDA(c, cudaStreamWaitEvent(c->side_stream, c->ev_fork, 0));
+            }
             StreamSwap sw(c, fork ? c->side_stream : c->stream);
             if (want_edge) {
                 stage_begin(c, "canny");
@@ -683,13 +688,23 @@ int complexity_body(vqa_ctx *c, const uint8_t *bgr, int n, int h, int w, size_t 
                 stage_end(c, "dct");
             }
             if (fork) VQA_CUDA(c, cudaEventRecord(c->ev_join, c->stream));
-        }
+            return rc;
+        };
+#ifdef VQA_AB
+        static const bool side_at_l0 = getenv("VQA_SIDE_AT_L0") && atoi(getenv("VQA_SIDE_AT_L0"));
+#else
+        constexpr bool side_at_l0 = false;
+#endif
+        const int first_pair = has_prev ? 0 : 1;
+        const bool hook_side = side_at_l0 && fork && want_motion && m - first_pair > 0;
+        std::function<int()> hook = side_chain;
+        if (!hook_side) if ((rc = side_chain())) return rc;
         // ---- Farneback motion
         if (want_motion) {
             stage_begin(c, "motion");
             const int first = has_prev ? 0 : 1;
             if (m - first > 0)
-                if ((rc = run_farneback(c, G + (size_t)first * HW, m - first, h, w, d_mag + s + first, nullptr))) return rc;
+                if ((rc = run_farneback(c, G + (size_t)first * HW, m - first, h, w, d_mag + s + first, nullptr, hook_side ? &hook : nullptr))) return rc;
             stage_end(c, "motion");
         }
         if (fork) VQA_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));     // join before gray / staging are reused

@@ -888,7 +888,8 @@ static void make_poly(PolyConst &pc)
 constexpr bool FB_DUAL_STREAMS = false;            // two-stream staggered schedule of a level (see run_farneback)
 constexpr bool FB_FUSE_NEXT = false;               // iterations 0 and 1 of a level: the blur evaluates the next UpdateMatrices itself
 
-int run_farneback(vqa_ctx *c, const uint8_t *gray, int npairs, int h, int w, double *mag_sum, float *flow_out)
+int run_farneback(vqa_ctx *c, const uint8_t *gray, int npairs, int h, int w, double *mag_sum, float *flow_out,
+                  const std::function<int()> *level0_hook)
 {
     if (npairs <= 0) return VQA_OK;
     const int nf = npairs + 1;
@@ -976,6 +977,8 @@ int run_farneback(vqa_ctx *c, const uint8_t *gray, int npairs, int h, int w, dou
         VQA_LAUNCH(c, k_fb_polyexp, gE, 256, PE_SMEM, I, lh, lw, pc, R4, Rs);
         // One group of pairs through the three iterations of the level, on the context's current stream.  `after_first`
         // is recorded behind the group's first kernel (the stagger of the two-stream schedule below).
+        if (k == 0 && level0_hook)
+            if (int rc = (*level0_hook)()) return rc;
         const size_t lpx = (size_t)lw * lh, ppx = (size_t)pw * ph;
         auto run_group = [&](int g0, int gn, size_t m0, cudaEvent_t after_first) -> int {
             // frame g0 of R, pair m0 of M (M is scratch: groups of the sequential schedule reuse pair 0 onwards), pair g0 of the flows

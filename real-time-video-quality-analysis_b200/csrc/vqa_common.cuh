@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <functional>
 #include <map>
 #include <string>
 #include <vector>
@@ -269,7 +270,8 @@ int run_dct_umma(vqa_ctx *c, const uint8_t *x, int n, int h, int w, float *coef,
 void dct_umma_release(vqa_ctx *c);
 // farneback.cu
 int run_farneback(vqa_ctx *c, const uint8_t *gray /* [n+1][h][w] */, int npairs, int h, int w,
-                  double *mag_sum /* [npairs] dev: sum |flow| */, float *flow_out /* optional, level-0 flow of pair 0.. */);
+                  double *mag_sum /* [npairs] dev: sum |flow| */, float *flow_out /* optional, level-0 flow of pair 0.. */,
+                  const std::function<int()> *level0_hook = nullptr /* called once, before the first UpdateMatrices of level 0 */);
 // psnr_ssim.cu
 int run_psnr_ssim_plane(vqa_ctx *c, const uint8_t *a, const uint8_t *b, int n, int h, int w, int stride, size_t frame_stride,
                         unsigned long long *sse /* [n] */, double *ssim_sum /* [n] */);
