@@ -26,15 +26,17 @@ namespace vqa {
 constexpr int UM_BM = 128, UM_BK = 64, UM_THREADS = 192;
 
 
-template <int BN, int MODE>
+// BK = K elements per shared-memory stage: 64 (128-byte rows, SWIZZLE_128B) or 32 (64-byte rows, SWIZZLE_64B: half the
+// bytes per stage, so a wider N tile still has >= 4 stages in flight)
+template <int BN, int MODE, int BK = UM_BK>
 struct UmmaCfg {
     static constexpr int A_PARTS = 2;
     static constexpr int B_PARTS = MODE == 1 ? 1 : 2;
-    static constexpr int A_BYTES = UM_BM * UM_BK * 2;
-    static constexpr int B_BYTES = BN * UM_BK * 2;
+    static constexpr int A_BYTES = UM_BM * BK * 2;
+    static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_PARTS * A_BYTES + B_PARTS * B_BYTES;
     static constexpr int STAGES = (208 * 1024) / STAGE_BYTES;
-    static constexpr int TMEM_COLS = 2 * BN;
+    static constexpr int TMEM_COLS = 2 * BN <= 256 ? 256 : 512;      // two accumulators; allocations are powers of two
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
 };
 
@@ -115,10 +117,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 UMMA): start address >> 4,
 // LBO = 0 (one 128-byte atom along K), SBO = 8 rows * 128 B = 1024 B, version 1, layout type 2.
+// BK = 32: SWIZZLE_64B, SBO = 8 rows * 64 B = 512 B, layout type 4.
+template <int BK = UM_BK>
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr)
 {
     const uint32_t lo = (smem_addr & 0x3FFFFu) >> 4;
-    const uint32_t hi = 64u | (1u << 14) | (2u << 29);
+    const uint32_t hi = BK == 64 ? (64u | (1u << 14) | (2u << 29)) : (32u | (1u << 14) | (4u << 29));
     return ((uint64_t)hi << 32) | lo;
 }
 
@@ -138,13 +142,13 @@ struct UmmaOut {
     double *energy;              // MODE 2: [frame]
 };
 
-template <int BN, int MODE>
+template <int BN, int MODE, int BK = UM_BK>
 __global__ void __launch_bounds__(UM_THREADS, 1)
 k_dct_umma(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
            const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1, int M, int N, int K,
            int nframes, UmmaOut out)
 {
-    using Cfg = UmmaCfg<BN, MODE>;
+    using Cfg = UmmaCfg<BN, MODE, BK>;
     constexpr int S = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -169,7 +173,7 @@ k_dct_umma(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUt
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int m_tiles = (M + UM_BM - 1) / UM_BM, n_tiles = (N + BN - 1) / BN, k_blocks = (K + UM_BK - 1) / UM_BK;
+    const int m_tiles = (M + UM_BM - 1) / UM_BM, n_tiles = (N + BN - 1) / BN, k_blocks = (K + BK - 1) / BK;
     const int tiles_per_frame = m_tiles * n_tiles, total = tiles_per_frame * nframes;
     const uint32_t smem_base = smem_u32(smem);
 
@@ -187,10 +191,10 @@ k_dct_umma(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUt
                     const uint32_t fb = smem_u32(&full[s]);
                     const uint32_t st = smem_base + (uint32_t)s * Cfg::STAGE_BYTES;
                     mbar_expect_tx(fb, Cfg::STAGE_BYTES);
-                    tma_load_2d(st, &tmA0, fb, kb * UM_BK, mb * UM_BM);
-                    tma_load_2d(st + Cfg::A_BYTES, &tmA1, fb, kb * UM_BK, mb * UM_BM);
-                    tma_load_3d(st + 2 * Cfg::A_BYTES, &tmB0, fb, kb * UM_BK, nb * BN, frame);
-                    if (MODE == 2) tma_load_3d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &tmB1, fb, kb * UM_BK, nb * BN, frame);
+                    tma_load_2d(st, &tmA0, fb, kb * BK, mb * UM_BM);
+                    tma_load_2d(st + Cfg::A_BYTES, &tmA1, fb, kb * BK, mb * UM_BM);
+                    tma_load_3d(st + 2 * Cfg::A_BYTES, &tmB0, fb, kb * BK, nb * BN, frame);
+                    if (MODE == 2) tma_load_3d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &tmB1, fb, kb * BK, nb * BN, frame);
                 }
                 __syncwarp();
             }
@@ -212,10 +216,10 @@ k_dct_umma(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUt
                 tc_fence_after();
                 if (lane == 0) {
                     const uint32_t st = smem_base + (uint32_t)s * Cfg::STAGE_BYTES;
-                    const uint64_t a0 = umma_desc(st), a1 = umma_desc(st + Cfg::A_BYTES);
-                    const uint64_t b0 = umma_desc(st + 2 * Cfg::A_BYTES), b1 = umma_desc(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES);
+                    const uint64_t a0 = umma_desc<BK>(st), a1 = umma_desc<BK>(st + Cfg::A_BYTES);
+                    const uint64_t b0 = umma_desc<BK>(st + 2 * Cfg::A_BYTES), b1 = umma_desc<BK>(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES);
 #pragma unroll
-                    for (int k = 0; k < UM_BK / 16; k++) {
+                    for (int k = 0; k < BK / 16; k++) {
                         const uint64_t adv = (uint64_t)(k * 2);          // 16 bf16 = 32 bytes = 2 x 16-byte units
                         const uint32_t first = (kb | k) ? 1u : 0u;
                         umma_bf16(d_tmem, a0 + adv, b0 + adv, idesc, first);
@@ -444,21 +448,24 @@ void dct_umma_release(vqa_ctx *c)
 
 // rows x K bf16, row pitch ld elements; optional frame dimension.
 static int make_map(vqa_ctx *c, UmmaState *s, CUtensorMap *m, const void *base, int K, int rows, int ld, int frames,
-                    size_t frame_stride_elems, int box_rows)
+                    size_t frame_stride_elems, int box_rows, int bk = UM_BK)
 {
     cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)(frames > 0 ? frames : 1)};
     cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)frame_stride_elems * 2};
-    cuuint32_t box[3] = {(cuuint32_t)UM_BK, (cuuint32_t)box_rows, 1};
+    cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     const int rank = frames > 0 ? 3 : 2;
     CUresult r = s->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void *>(base), dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_err(c, VQA_E_CUDA, "cuTensorMapEncodeTiled failed (%d): K=%d rows=%d ld=%d", (int)r, K, rows, ld);
     return VQA_OK;
 }
 
 static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+constexpr bool DCT_GEMM2_WIDE = false;             // development build: GEMM 2 on wide tiles with 32-element K stages (see run_dct_umma)
 
 int run_dct_umma(vqa_ctx *c, const uint8_t *x, int n, int h, int w, float *coef, double *energy,
                  const unsigned long long *pixel_sums)
@@ -470,6 +477,9 @@ int run_dct_umma(vqa_ctx *c, const uint8_t *x, int n, int h, int w, float *coef,
     UmmaState *s;
     int rc = get_state(c, &s);
     if (rc) return rc;
+#ifdef VQA_AB
+    const bool gemm2_wide = getenv("VQA_DCT_G2W") ? atoi(getenv("VQA_DCT_G2W")) != 0 : DCT_GEMM2_WIDE;
+#endif
     const int ldw = round_up(w, 64), ldh = round_up(h, 64);
     VQA_BUF(c, Dw_hi, __nv_bfloat16, "umma.Dw_hi", (size_t)w * ldw);
     VQA_BUF(c, Dw_lo, __nv_bfloat16, "umma.Dw_lo", (size_t)w * ldw);
@@ -520,17 +530,31 @@ int run_dct_umma(vqa_ctx *c, const uint8_t *x, int n, int h, int w, float *coef,
         VQA_LAUNCH(c, (k_dct_umma<BN1, 1>), grid, UM_THREADS, (UmmaCfg<BN1, 1>::SMEM_BYTES), mA0, mA1, mB0, mB1, w, h, w, n, o1);
     }
     // GEMM 2: C[h x w] = Dh[h x h] * T ; A rows = h, K = h ; B = T^T rows = w, K = h, per frame
-    if ((rc = make_map(c, s, &mA0, Dh_hi, h, h, ldh, 0, 0, UM_BM))) return rc;
-    if ((rc = make_map(c, s, &mA1, Dh_lo, h, h, ldh, 0, 0, UM_BM))) return rc;
-    if ((rc = make_map(c, s, &mB0, Tt_hi, h, w, ldh, n, (size_t)w * ldh, BN2))) return rc;
-    if ((rc = make_map(c, s, &mB1, Tt_lo, h, w, ldh, n, (size_t)w * ldh, BN2))) return rc;
     UmmaOut o2{};
     o2.C = coef; o2.ldc = w; o2.c_frame_stride = (size_t)h * w; o2.energy = energy;
+    VQA_BYTES(c, (4.0 * w * h + 4.0 * w * h) * n);
+    VQA_FLOPS(c, 3.0 * 2.0 * h * h * w * n);
+#ifdef VQA_AB                                                        // measured slower (profiles/r02_notes.md 14): development build only
+    if (gemm2_wide) {
+        // 128 x 256 tiles on 32-element K stages (SWIZZLE_64B): 48 KB per stage, 4 stages; 128 flop per staged byte instead of 96
+        constexpr int BNW = 256, BKW = 32;
+        VQA_CUDA(c, cudaFuncSetAttribute(k_dct_umma<BNW, 2, BKW>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<BNW, 2, BKW>::SMEM_BYTES));
+        if ((rc = make_map(c, s, &mA0, Dh_hi, h, h, ldh, 0, 0, UM_BM, BKW))) return rc;
+        if ((rc = make_map(c, s, &mA1, Dh_lo, h, h, ldh, 0, 0, UM_BM, BKW))) return rc;
+        if ((rc = make_map(c, s, &mB0, Tt_hi, h, w, ldh, n, (size_t)w * ldh, BNW, BKW))) return rc;
+        if ((rc = make_map(c, s, &mB1, Tt_lo, h, w, ldh, n, (size_t)w * ldh, BNW, BKW))) return rc;
+        const int tiles = cdiv(h, UM_BM) * cdiv(w, BNW) * n;
+        const int grid = tiles < c->sm_count ? tiles : c->sm_count;
+        VQA_LAUNCH(c, (k_dct_umma<BNW, 2, BKW>), grid, UM_THREADS, (UmmaCfg<BNW, 2, BKW>::SMEM_BYTES), mA0, mA1, mB0, mB1, h, w, h, n, o2);
+    } else
+#endif
     {
+        if ((rc = make_map(c, s, &mA0, Dh_hi, h, h, ldh, 0, 0, UM_BM))) return rc;
+        if ((rc = make_map(c, s, &mA1, Dh_lo, h, h, ldh, 0, 0, UM_BM))) return rc;
+        if ((rc = make_map(c, s, &mB0, Tt_hi, h, w, ldh, n, (size_t)w * ldh, BN2))) return rc;
+        if ((rc = make_map(c, s, &mB1, Tt_lo, h, w, ldh, n, (size_t)w * ldh, BN2))) return rc;
         const int tiles = cdiv(h, UM_BM) * cdiv(w, BN2) * n;
         const int grid = tiles < c->sm_count ? tiles : c->sm_count;
-        VQA_BYTES(c, (4.0 * w * h + 4.0 * w * h) * n);
-        VQA_FLOPS(c, 3.0 * 2.0 * h * h * w * n);
         VQA_LAUNCH(c, (k_dct_umma<BN2, 2>), grid, UM_THREADS, (UmmaCfg<BN2, 2>::SMEM_BYTES), mA0, mA1, mB0, mB1, h, w, h, n, o2);
     }
     VQA_LAUNCH(c, k_dc_fix, cdiv(n, 128), 128, 0, coef, (size_t)h * w, h, w, n, sums, energy);
