@@ -10,7 +10,8 @@ def norm(name):
     n = name.split("(const")[0].split("(unsigned")[0].split("(float")[0].split("(int")[0].split("(double")[0].split("(CUtensorMap")[0]
     n = n.replace("void ", "").replace("vqa::", "").replace("(int)", "").replace("(bool)", "").replace(" ", "")
     n = n.split("(")[0]
-    n = n.replace("k_dct_umma<256,1>", "k_dct_umma<BN1,1>").replace("k_dct_umma<128,2>", "k_dct_umma<BN2,2>")
+    n = re.sub(r"k_dct_umma<256,1(,64)?>", "k_dct_umma<BN1,1>", n)
+    n = re.sub(r"k_dct_umma<128,2(,64)?>", "k_dct_umma<BN2,2>", n)
     n = re.sub(r"k_fb_pyramid_dec<[0-9,]+>", "k_fb_pyramid_dec<S,R,TO>", n)
     n = re.sub(r"<1>$", "<true>", n) if n.startswith(("k_yuv420_gray_hist", "k_gray_hist", "k_orb64")) else n
     n = re.sub(r"<0>$", "<false>", n) if n.startswith(("k_yuv420_gray_hist", "k_gray_hist", "k_orb64")) else n
