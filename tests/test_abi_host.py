@@ -202,3 +202,25 @@ def test_drop_in_module_names_resolve_from_the_package_dir():
             "print(c.calculate_average_scene_complexity.__name__, v.run_ffmpeg_metrics.__name__)" % PKG)
     out = subprocess.check_output([sys.executable, "-c", code], text=True, stderr=subprocess.DEVNULL)
     assert out.split() == ["calculate_average_scene_complexity", "run_ffmpeg_metrics"]
+
+
+def test_product_build_reads_no_environment():
+    """Every getenv of csrc/ sits inside `#ifdef VQA_AB` (the development build of the A/B notes): the product library's
+    numerics and speed cannot be changed from the environment (round-1 finding: 14 knobs lived in the hot path)."""
+    csrc = os.path.join(PKG, "csrc")
+    bad = []
+    for name in sorted(os.listdir(csrc)):
+        if not name.endswith((".cu", ".cuh")):
+            continue
+        depth_ab, stack = 0, []
+        for ln, line in enumerate(open(os.path.join(csrc, name)), 1):
+            t = line.strip()
+            if t.startswith(("#ifdef", "#ifndef", "#if ")):
+                stack.append("VQA_AB" in t and t.startswith("#ifdef"))
+            elif t.startswith("#else") and stack:
+                stack[-1] = False                      # the #else branch of an #ifdef VQA_AB is product code
+            elif t.startswith("#endif") and stack:
+                stack.pop()
+            if "getenv" in t and not t.startswith("//") and not any(stack):
+                bad.append("%s:%d" % (name, ln))
+    assert not bad, bad
